@@ -1,0 +1,118 @@
+"""Pins the CPU oracle to the reference: oracle outputs vs golden vectors produced by running
+the reference's own modules (tests/golden/make_golden.py).  Indices must be equal except on
+provable near-ties (top-2 margin below 1e-5), floats within 1e-4 relative."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import xq_oracle as xo
+
+RTOL = 2e-4
+
+
+def close(a, b, rtol=RTOL, atol=None):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if atol is None:
+        atol = rtol * max(1e-30, float(np.abs(b).max()))
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def check_idx(mine, ref, margin, tie=1e-5):
+    mine, ref = np.asarray(mine).reshape(-1), np.asarray(ref).reshape(-1)
+    bad = mine != ref
+    if bad.any():
+        assert np.all(np.asarray(margin).reshape(-1)[bad] < tie), "index mismatch that is not a near-tie"
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("name", ["vq4096_b1", "vq512_randn", "vq300_nonorm"])
+def test_vq_forward_backward(name):
+    g = load_golden(name)
+    cn = bool(g["codebook_norm"])
+    fwd = xo.vq_forward(g["z"], g["E"], beta=float(g["beta"]), codebook_norm=cn)
+    assert check_idx(fwd["idx"], g["idx"], fwd["margin"]) == 0
+    close(fwd["out"], g["out"])
+    close(fwd["q_nchw"], g["fhat"])
+    close(fwd["vq"], g["vq"])
+    close(fwd["commit"], g["commit"])
+    gz, gE = xo.vq_backward(fwd, g["E"], g["g_out"], float(g["w_vq"]), float(g["w_commit"]), float(g["beta"]), cn)
+    close(gz, g["gz"])
+    gE_ref = np.zeros_like(gE)
+    gE_ref[g["gE_rows"]] = g["gE_vals"]
+    close(gE, gE_ref)
+    # EMA / usage after `steps` identical forwards (xqgan_model.py:773-788)
+    ema = np.zeros(g["E"].shape[0], np.float32)
+    for s in range(int(g["steps"])):
+        ema = xo.ema_update(ema, fwd["hist"], s)
+    close(ema, g["ema"], rtol=1e-6)
+    N = g["z"].size // g["z"].shape[1]
+    margin = 1 * N / g["E"].shape[0] * 0.08
+    assert abs(float((ema >= margin).mean() * 100) - float(g["usage"])) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["perturb_a07", "perturb_a0"])
+def test_add_perturbation(name):
+    g = load_golden(name)
+    cn = bool(g["codebook_norm"])
+    fwd = xo.add_perturbation(g["z"], g["zq"], g["E"], cn, float(g["alpha"]), float(g["beta"]), int(g["delta"]),
+                              g["rand_u"], g["rand_j"])
+    close(fwd["out"], g["out"])
+    gz, gzq = xo.add_perturbation_backward(fwd, g["g"], cn)
+    close(gz, g["gz"], atol=1e-6)
+    close(gzq, g["gzq"])
+
+
+@pytest.mark.parametrize("name", ["msvr_small", "msvr_4096", "msvr_l2", "msvr_shared1"])
+def test_vq2(name):
+    g = load_golden(name)
+    pn = [int(p) for p in g["patch_nums"]]
+    zn = bool(g["using_znorm"])
+    fwd = xo.vq2_forward(g["f"], g["E"], g["phi_w"], g["phi_b"], pn, using_znorm=zn, codebook_drop=float(g["codebook_drop"]),
+                         dropout=g["dropout"])
+    for si in range(len(pn)):
+        assert check_idx(fwd["idx"][si], g[f"idx{si}"], fwd["margins"][si]) == 0
+    close(fwd["out"], g["out"])
+    close(fwd["vq"], g["vq"])
+    close(fwd["commit"], g["commit"])
+    gf, gE, gw, gb = xo.vq2_backward(fwd, g["f"], g["E"], g["phi_w"], g["phi_b"], pn, g["g_out"], float(g["w_vq"]),
+                                     float(g["w_commit"]))
+    close(gf, g["gf"])
+    close(gE, g["gE"])
+    close(gw, g["gphi_w"])
+    close(gb, g["gphi_b"])
+    fh = xo.vq2_f_to_idxBl_or_fhat(g["f"], g["E"], g["phi_w"], g["phi_b"], pn, using_znorm=zn, to_fhat=True)
+    close(fh[-1], g["fhat_last"])
+    close(fh[len(pn) // 2], g["fhat_mid"])
+    # EMA rows: record_hit increments once per scale (quant.py:121-127)
+    SN, V = len(pn), g["E"].shape[0]
+    ema = np.zeros((SN, V), np.float32)
+    rec = 0
+    for _ in range(int(g["steps"])):
+        for si in range(SN):
+            ema[si] = xo.ema_update(ema[si], fwd["hist"][si], rec)
+            rec += 1
+    close(ema, g["ema"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["msbr_small", "msbr_14", "lfq_nonorm"])
+def test_lfq(name):
+    g = load_golden(name)
+    pn = [int(p) for p in g["patch_nums"]]
+    zn = bool(g["using_znorm"])
+    kw = dict(using_znorm=zn, codebook_drop=float(g["codebook_drop"]), dropout=g["dropout"], scale=float(g["scale"]),
+              entropy_weight=float(g["entropy_weight"]))
+    fwd = xo.lfq_forward(g["f"], g["phi_w"], g["phi_b"], pn, **kw)
+    close(fwd["scaler"], g["scaler"], rtol=1e-6)
+    for si in range(len(pn)):
+        np.testing.assert_array_equal(fwd["idx"][si], g[f"idx{si}"])
+    close(fwd["out"], g["out"])
+    close(fwd["vq"], g["vq"])
+    close(fwd["commit"], g["commit"])
+    close(fwd["entropy"], g["entropy"])
+    gf, gw, gb = xo.lfq_backward(fwd, g["f"], g["phi_w"], g["phi_b"], pn, g["g_out"], float(g["w_vq"]),
+                                 float(g["w_commit"]), float(g["w_ent"]), using_znorm=zn,
+                                 entropy_weight=float(g["entropy_weight"]))
+    close(gf, g["gf"])
+    close(gw, g["gphi_w"])
+    close(gb, g["gphi_b"])
