@@ -1,0 +1,145 @@
+"""ctypes binding of libxqb200.so (include/xqb200.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, this module raises.
+The product never imports anything under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libxqb200.so")
+XQ_MAX_SCALES = 32
+
+XQ_MS_VQ_ZNORM, XQ_MS_VQ_L2, XQ_MS_BSQ = 0, 1, 2
+
+
+class XqMsDesc(ctypes.Structure):
+    _fields_ = [
+        ("B", c_int), ("C", c_int), ("H", c_int), ("W", c_int),
+        ("V", c_int), ("K", c_int), ("SN", c_int), ("mode", c_int),
+        ("patch_nums", c_int * XQ_MAX_SCALES),
+        ("phi_map", c_int * XQ_MAX_SCALES),
+        ("scaler", c_float * XQ_MAX_SCALES),
+        ("resi_ratio", c_float), ("beta", c_float),
+        ("loss_div_sn_all", c_int), ("channel_norm", c_int),
+        ("entropy_weight", c_float), ("w_sample", c_float), ("w_batch", c_float),
+    ]
+
+
+class XqError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libxqb200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XqError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is required (there is no CPU/PyTorch fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or imagefolder_b200/csrc/build.sh")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, f32p, i64p = c_void_p, c_void_p, c_void_p  # device pointers are passed as integers
+    L.xq_strerror.restype = ctypes.c_char_p
+    L.xq_strerror.argtypes = [c_int]
+    L.xq_last_cuda_error.restype = ctypes.c_char_p
+    L.xq_abi_version.restype = c_int
+    L.xq_vq_workspace_bytes.restype = c_size_t
+    L.xq_vq_workspace_bytes.argtypes = [c_int] * 4
+    L.xq_vq_forward.restype = c_int
+    L.xq_vq_forward.argtypes = [f32p, f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, i64p, f32p, f32p, f32p,
+                                vp, c_size_t, vp]
+    L.xq_vq_backward.restype = c_int
+    L.xq_vq_backward.argtypes = [f32p, f32p, i64p, f32p, f32p, f32p, c_int, c_int, c_int, c_int, c_int, c_float, f32p,
+                                 f32p, vp]
+    L.xq_perturb_workspace_bytes.restype = c_size_t
+    L.xq_perturb_workspace_bytes.argtypes = [c_int] * 4
+    L.xq_perturb_forward.restype = c_int
+    L.xq_perturb_forward.argtypes = [f32p, f32p, f32p, f32p, i64p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                     c_int, f32p, i64p, vp, c_size_t, vp]
+    L.xq_perturb_backward.restype = c_int
+    L.xq_perturb_backward.argtypes = [f32p, f32p, c_int, c_int, c_int, c_int, c_int, f32p, f32p, vp]
+    dp = POINTER(XqMsDesc)
+    L.xq_ms_workspace_bytes.restype = c_size_t
+    L.xq_ms_workspace_bytes.argtypes = [dp]
+    L.xq_ms_saved_bytes.restype = c_size_t
+    L.xq_ms_saved_bytes.argtypes = [dp]
+    L.xq_ms_total_tokens.restype = c_int64
+    L.xq_ms_total_tokens.argtypes = [dp]
+    L.xq_ms_forward.restype = c_int
+    L.xq_ms_forward.argtypes = [dp, f32p, f32p, f32p, f32p, f32p, c_int, f32p, i64p, f32p, f32p, f32p, vp, vp,
+                                c_size_t, vp]
+    L.xq_ms_backward.restype = c_int
+    L.xq_ms_backward.argtypes = [dp, f32p, f32p, f32p, f32p, f32p, i64p, vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                 f32p, vp, c_size_t, vp]
+    L.xq_ms_decode.restype = c_int
+    L.xq_ms_decode.argtypes = [dp, i64p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    L.xq_usage_ema.restype = c_int
+    L.xq_usage_ema.argtypes = [f32p, f32p, c_int, c_int, c_int, c_float, f32p, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    L = lib()
+    msg = L.xq_strerror(rc).decode()
+    if rc == -3:
+        msg += ": " + L.xq_last_cuda_error().decode()
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise XqError(f"{what}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be a contiguous CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise XqError("libxqb200 needs CUDA tensors: there is no CPU path (got a %s tensor)" % t.device)
+    if not t.is_contiguous():
+        raise XqError("libxqb200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def make_ms_desc(B, C, H, W, V, K, patch_nums, phi_map, mode, scaler=None, resi_ratio=0.5, beta=0.25,
+                 loss_div_sn_all=False, channel_norm=False, entropy_weight=0.0, w_sample=1.0, w_batch=1.0) -> XqMsDesc:
+    SN = len(patch_nums)
+    if SN > XQ_MAX_SCALES:
+        raise ValueError(f"at most {XQ_MAX_SCALES} scales are supported")
+    d = XqMsDesc()
+    d.B, d.C, d.H, d.W, d.V, d.K, d.SN, d.mode = int(B), int(C), int(H), int(W), int(V), int(K), SN, int(mode)
+    for i, p in enumerate(patch_nums):
+        d.patch_nums[i] = int(p)
+        d.phi_map[i] = int(phi_map[i]) if K > 0 else -1
+        d.scaler[i] = float(scaler[i]) if scaler is not None else 0.0
+    d.resi_ratio, d.beta = float(resi_ratio), float(beta)
+    d.loss_div_sn_all, d.channel_norm = int(bool(loss_div_sn_all)), int(bool(channel_norm))
+    d.entropy_weight, d.w_sample, d.w_batch = float(entropy_weight), float(w_sample), float(w_batch)
+    return d
+
+
+EXPORTED_SYMBOLS = [
+    "xq_strerror", "xq_abi_version", "xq_last_cuda_error", "xq_vq_workspace_bytes", "xq_vq_forward",
+    "xq_vq_backward", "xq_perturb_workspace_bytes", "xq_perturb_forward", "xq_perturb_backward",
+    "xq_ms_workspace_bytes", "xq_ms_saved_bytes", "xq_ms_total_tokens", "xq_ms_forward", "xq_ms_backward",
+    "xq_ms_decode", "xq_usage_ema",
+]

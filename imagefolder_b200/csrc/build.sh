@@ -1,0 +1,12 @@
+#!/bin/bash
+# Build libxqb200.so (sm_100a only).  -fmad=false: canonical arithmetic, see xq_common.cuh.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/../lib"
+mkdir -p "$OUT"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false --compiler-options -fPIC"
+nvcc $FLAGS -c "$HERE/vq_kernels.cu" -o "$OUT/vq_kernels.o" "$@" &
+nvcc $FLAGS -c "$HERE/ms_kernels.cu" -o "$OUT/ms_kernels.o" "$@" &
+wait
+nvcc -shared -o "$OUT/libxqb200.so" "$OUT/vq_kernels.o" "$OUT/ms_kernels.o" -lcudart
+echo "$OUT/libxqb200.so"

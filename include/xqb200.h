@@ -1,0 +1,177 @@
+/*
+ * xqb200.h -- C ABI of libxqb200.so: the B200 (sm_100a) quantizer hot path of the XQ-GAN /
+ * ImageFolder image tokenizer.
+ *
+ * The reference (lxa9867/ImageFolder) is pure Python; its "operator boundary" for this path is
+ * the nn.Module surface of its quantizers.  Each entry point below replaces
+ * the arithmetic of one reference method and is what a binding for that method calls
+ * (INTEGRATION.md shows the ctypes stubs; imagefolder_b200/_capi.py is the in-repo binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch), contiguous, fp32 unless stated; indices are int64 like torch.long.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - no allocation, no global state: scratch memory is a caller-provided workspace whose size the
+ *     matching *_workspace_bytes() call returns; calls are re-entrant across streams when the
+ *     workspaces differ.
+ *   - return value: 0 = ok, negative = error (xq_strerror()); the Python side maps it to
+ *     RuntimeError / ValueError, mirroring the reference's exceptions/asserts.
+ *   - tensors named `*_nchw` are [B, C, H*W] exactly as the reference passes them (B,C,H,W
+ *     contiguous); "rows" n = b*HW + p follow the reference's 'b c h w -> b h w c' flattening
+ *     (xqgan_model.py:750-751).
+ */
+#ifndef XQB200_H_
+#define XQB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XQ_OK 0
+#define XQ_ERR_ARG (-1)         /* bad shape / null pointer / unsupported size */
+#define XQ_ERR_WORKSPACE (-2)   /* workspace too small */
+#define XQ_ERR_CUDA (-3)        /* a CUDA runtime call or launch failed */
+#define XQ_ERR_UNSUPPORTED (-4) /* valid in the reference, not built here */
+
+#define XQ_MAX_SCALES 32
+
+const char *xq_strerror(int code);
+int xq_abi_version(void);
+/* last CUDA error string recorded on this thread by a failed call (for diagnostics) */
+const char *xq_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-scale VectorQuantizer   (VQ-4096 / VQ-8192 / VP2-* / RobustTok)
+ *   replaces VectorQuantizer.forward           tokenizer/tokenizer_image/xqgan_model.py:745-801
+ *            VectorQuantizer.f_to_idxBl_or_fhat                      xqgan_model.py:803-833
+ * ------------------------------------------------------------------------------------------ */
+size_t xq_vq_workspace_bytes(int B, int C, int HW, int V);
+
+/*
+ * Fused normalise -> distance -> argmin -> gather -> normalise -> STE value -> MSE partials
+ * -> usage histogram.  The N x V distance matrix is never written to memory.
+ *   z_nchw        [B,C,HW]   encoder latent (input of the reference forward)
+ *   E             [V,C]      embedding.weight (raw)
+ *   codebook_norm 1: rows and codes are L2-normalised first (xqgan_model.py:753-756)
+ *   ste_value     1: out = zn + (q - zn)  (forward, :796)   0: out = q  (f_to_idxBl_or_fhat :826-831)
+ *   idx           [B*HW]     argmin index per row (first index on ties)
+ *   out_nchw      [B,C,HW]
+ *   loss          [2]        {vq_loss, commit_loss} = {mse, beta*mse} (:792-793); may be NULL
+ *   hist          [V]        += bincount(idx) as float (:774); may be NULL
+ */
+int xq_vq_forward(const float *z_nchw, const float *E, int B, int C, int HW, int V, int codebook_norm,
+                  int ste_value, float beta, int64_t *idx, float *out_nchw, float *loss, float *hist,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward of (out, vq_loss, commit_loss) wrt z and E.
+ *   g_out_nchw [B,C,HW] or NULL; g_vq / g_commit: device scalars or NULL (treated as 0)
+ *   gz_nchw    [B,C,HW]  written;   gE [V,C] overwritten (zeroed, then scatter-added)
+ */
+int xq_vq_backward(const float *z_nchw, const float *E, const int64_t *idx, const float *g_out_nchw,
+                   const float *g_vq, const float *g_commit, int B, int C, int HW, int V, int codebook_norm,
+                   float beta, float *gz_nchw, float *gE, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Latent perturbation   (RobustTok)
+ *   replaces add_perturbation      tokenizer/tokenizer_image/latent_perturbation.py:4-35
+ * The two random tensors the reference draws (torch.rand(N) :21, torch.randint(0,delta,(N,)) :22)
+ * are INPUTS, so the host keeps the reference's RNG stream.
+ * ------------------------------------------------------------------------------------------ */
+size_t xq_perturb_workspace_bytes(int B, int C, int HW, int V);
+/*   n_perturb = int(B * beta) evaluated by the host (Python double arithmetic, :32)
+ *   out_nchw [B,C,HW] = where(b < n_perturb, zn + (normalize(E[sel]) - zn), zq)
+ *   sel      [n_perturb*HW] chosen code per perturbed row (may be NULL) */
+int xq_perturb_forward(const float *z_nchw, const float *zq_nchw, const float *E, const float *rand_u,
+                       const int64_t *rand_j, int B, int C, int HW, int V, int codebook_norm, float alpha,
+                       int n_perturb, int delta, float *out_nchw, int64_t *sel, void *workspace,
+                       size_t workspace_bytes, void *stream);
+/*   g [B,C,HW] -> gz (through the normalisation Jacobian, perturbed samples only), gzq (the rest) */
+int xq_perturb_backward(const float *z_nchw, const float *g_nchw, int B, int C, int HW, int codebook_norm,
+                        int n_perturb, float *gz_nchw, float *gzq_nchw, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale residual quantizers (MSVR*, MSBR*)
+ *   replaces VectorQuantizer2.forward / f_to_idxBl_or_fhat   tokenizer/tokenizer_image/quant.py:64-223
+ *            LFQ.forward / f_to_idxBl_or_fhat    tokenizer/tokenizer_image/lookup_free_quantize.py:149-380
+ *            Phi.forward                                                   quant.py:261-268
+ * One CTA owns one image: residual, accumulated f_hat and the upsampled code map stay in shared
+ * memory across all scales.
+ * ------------------------------------------------------------------------------------------ */
+#define XQ_MS_VQ_ZNORM 0 /* VectorQuantizer2, using_znorm=True  (argmax cosine)        */
+#define XQ_MS_VQ_L2 1    /* VectorQuantizer2, using_znorm=False (argmin L2)            */
+#define XQ_MS_BSQ 2      /* LFQ: sign bits, code = +-scaler[si]                        */
+
+typedef struct {
+    int B, C, H, W;       /* f is [B,C,H,W]                                             */
+    int V;                /* codebook size (BSQ: 2^C)                                   */
+    int K;                /* number of Phi modules (0 = identity)                       */
+    int SN;               /* number of scales                                           */
+    int mode;             /* XQ_MS_*                                                    */
+    int patch_nums[XQ_MAX_SCALES];
+    int phi_map[XQ_MAX_SCALES]; /* scale -> Phi index (PhiPartiallyShared, quant.py:279-288) */
+    float scaler[XQ_MAX_SCALES]; /* BSQ code magnitude per scale (lookup_free_quantize.py:124-128) */
+    float resi_ratio;     /* Phi blend r (quant.py:265)                                 */
+    float beta;           /* commit weight                                              */
+    int loss_div_sn_all;  /* 0: only vq is divided by SN (quant.py:134)  1: all (LFQ :238-240) */
+    int channel_norm;     /* 1: f is L2-normalised over C first (LFQ using_znorm, :153) */
+    float entropy_weight, w_sample, w_batch; /* LFQ entropy term                        */
+} xq_ms_desc;
+
+size_t xq_ms_workspace_bytes(const xq_ms_desc *d);
+size_t xq_ms_saved_bytes(const xq_ms_desc *d); /* bytes of `saved` (forward -> backward) */
+int64_t xq_ms_total_tokens(const xq_ms_desc *d); /* sum_si B*pn^2 */
+
+/*
+ *   f            [B,C,H,W]
+ *   E            [V,C] raw codebook (NULL for BSQ)
+ *   phi_w/phi_b  [K,C,C,3,3] / [K,C]
+ *   n_quantizers [B] float, scale si contributes to sample b iff si < n_quantizers[b]
+ *                (quant.py:79-86,115); NULL = no quantizer dropout
+ *   with_losses  0: inference (f_to_idxBl_or_fhat): no masks, no losses
+ *   out          [B,C,H,W]  forward: (f_hat - f) + f (quant.py:135); inference: f_hat
+ *   idx_all      [sum_si B*pn^2] int64, scale-major, then (b, y, x)
+ *   fhat_scales  [SN,B,C,H,W] cumulative f_hat after each scale, or NULL (to_fhat=True lists)
+ *   loss         [3] {vq, commit, entropy}
+ *   hist         [SN,V] += bincount per scale, or NULL
+ *   saved        xq_ms_saved_bytes(): state the backward needs (final masked f_hat, ...)
+ */
+int xq_ms_forward(const xq_ms_desc *d, const float *f, const float *E, const float *phi_w, const float *phi_b,
+                  const float *n_quantizers, int with_losses, float *out, int64_t *idx_all, float *fhat_scales,
+                  float *loss, float *hist, void *saved, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward wrt f, E, phi_w, phi_b.
+ *   g_out [B,C,H,W] or NULL; g_vq/g_commit/g_entropy device scalars or NULL
+ *   gf [B,C,H,W]; gE [V,C] (NULL for BSQ); gphi_w [K,C,C,3,3]; gphi_b [K,C]  -- all overwritten
+ */
+int xq_ms_backward(const xq_ms_desc *d, const float *f, const float *E, const float *phi_w, const float *phi_b,
+                   const float *n_quantizers, const int64_t *idx_all, const void *saved, const float *g_out,
+                   const float *g_vq, const float *g_commit, const float *g_entropy, float *gf, float *gE,
+                   float *gphi_w, float *gphi_b, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * VAR-side helpers built from the same primitives (quant.py:148-180, 226-258):
+ * given token indices per scale, rebuild f_hat (all scales) and the next-scale inputs.
+ *   var_input [B, sum_{si>=1} pn_si^2, C] (idxBl_to_var_input) or NULL
+ *   fhat_scales [SN,B,C,H,W] or NULL ; out [B,C,H,W] final f_hat or NULL
+ */
+int xq_ms_decode(const xq_ms_desc *d, const int64_t *idx_all, const float *E, const float *phi_w,
+                 const float *phi_b, float *out, float *fhat_scales, float *var_input, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Codebook-usage EMA (xqgan_model.py:777-788, quant.py:121-127,137-141)
+ *   ema[rows,V], hit[rows,V]: row i <- copy | 0.9/0.1 | 0.99/0.01 blend of hit[i], chosen by
+ *   (record_hit + i) == 0 | < 100 | otherwise  (the reference bumps record_hit once per scale).
+ *   usage_out[rows] (device, may be NULL) = 100 * mean(ema[i] >= margin)
+ * ------------------------------------------------------------------------------------------ */
+int xq_usage_ema(float *ema, const float *hit, int rows, int V, int record_hit, float margin,
+                 float *usage_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XQB200_H_ */

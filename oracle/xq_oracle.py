@@ -414,16 +414,22 @@ def _dh2(p):
     return -np.log(p + 1e-8) - p / (p + 1e-8) + np.log(1.0 - p + 1e-8) + (1.0 - p) / (1.0 - p + 1e-8)
 
 
+def lfq_scaler(SN: int, C: int, scale: float, using_znorm: bool) -> np.ndarray:
+    """lookup_free_quantize.py:124-128, in float32 like torch (scale ** arange, / sqrt(C))."""
+    scaler = np.power(np.float32(scale), np.arange(SN, dtype=np.float32)).astype(np.float32)
+    if using_znorm:
+        scaler = (scaler / np.float32(np.sqrt(C))).astype(np.float32)
+    return scaler
+
+
 def lfq_forward(f, phi_w, phi_b, patch_nums, using_znorm=False, beta=0.25, resi_ratio=0.5, codebook_drop=0.0,
-                dropout=None, scale=1.0, entropy_weight=0.1, w_sample=1.0, w_batch=1.0) -> Dict:
-    """LFQ.forward (lookup_free_quantize.py:149-250), training mode, soft_entropy=True."""
+                dropout=None, scale=1.0, entropy_weight=0.1, w_sample=1.0, w_batch=1.0, scaler=None) -> Dict:
+    """LFQ.forward (lookup_free_quantize.py:149-250), training mode, soft_entropy=True.
+    `scaler` (the module's registered buffer) overrides the value derived from `scale`."""
     f = _c32(f)
     B, C, H, W = f.shape
     SN = len(patch_nums)
-    scaler = (float(scale) ** np.arange(SN)).astype(np.float64)
-    if using_znorm:
-        scaler = scaler / np.sqrt(C)
-    scaler = scaler.astype(np.float32)
+    scaler = lfq_scaler(SN, C, scale, using_znorm) if scaler is None else np.asarray(scaler, np.float32)
     if using_znorm:  # F.normalize(f, dim=1)  :153
         rows = nchw_to_rows(f)
         fn_rows, fden = l2norm_rows(rows)

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/xqb200.h declares; argument validation returns error codes (no GPU work is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "xqb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(xq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 16
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/xqb200.h but not exported by libxqb200.so"
+    assert sorted(_capi.EXPORTED_SYMBOLS) == syms
+    assert L.xq_abi_version() == 1
+    assert L.xq_strerror(0) == b"ok"
+
+
+def test_desc_struct_layout_matches_header():
+    from imagefolder_b200 import _capi
+    # 8 ints + 3 arrays of 32 4-byte values + 2 floats + 2 ints + 3 floats
+    assert ctypes.sizeof(_capi.XqMsDesc) == 4 * (8 + 3 * 32 + 2 + 2 + 3)
+
+
+def test_argument_validation_without_gpu():
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    assert L.xq_vq_workspace_bytes(0, 32, 256, 8192) == 0
+    assert L.xq_vq_workspace_bytes(256, 32, 256, 8192) >= 4 * 8192 * 32
+    assert L.xq_vq_forward(None, None, 1, 1, 1, 1, 1, 1, 0.25, None, None, None, None, None, 0, None) == -1
+    d = _capi.make_ms_desc(2, 8, 5, 5, 64, 4, [1, 2, 5], [0, 1, 3], _capi.XQ_MS_VQ_ZNORM)
+    assert L.xq_ms_total_tokens(d) == 2 * (1 + 4 + 25)
+    assert L.xq_ms_workspace_bytes(d) > 0 and L.xq_ms_saved_bytes(d) == 4 * 2 * 8 * 25
+    bad = _capi.make_ms_desc(2, 8, 5, 5, 64, 4, [1, 2, 4], [0, 1, 3], _capi.XQ_MS_VQ_ZNORM)  # last scale != H
+    assert L.xq_ms_total_tokens(bad) == -1
+    bsq = _capi.make_ms_desc(2, 6, 3, 3, 100, 0, [1, 3], [0, 0], _capi.XQ_MS_BSQ)  # V != 2**C
+    assert L.xq_ms_workspace_bytes(bsq) == 0
+    with pytest.raises(ValueError):
+        _capi.check(-1, "x")
+    with pytest.raises(_capi.XqError):
+        _capi.check(-2, "x")
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    """no CPU fallback: the product refuses host tensors instead of silently computing elsewhere."""
+    import torch
+    from imagefolder_b200 import VectorQuantizer, _capi
+    q = VectorQuantizer(64, 8)
+    with pytest.raises(_capi.XqError):
+        q(torch.randn(1, 8, 2, 2))
+
+
+def test_state_dict_keys_match_reference():
+    from imagefolder_b200 import LFQ, VectorQuantizer, VectorQuantizer2
+    pn = [1, 2, 3]
+    assert set(VectorQuantizer(64, 8).state_dict()) == {"embedding.weight", "ema_vocab_hit_SV"}
+    k2 = set(VectorQuantizer2(64, 8, v_patch_nums=pn).state_dict())
+    assert k2 == {"ema_vocab_hit_SV", "embedding.weight"} | {f"quant_resi.qresi_ls.{i}.{n}" for i in range(4)
+                                                              for n in ("weight", "bias")}
+    kl = set(LFQ(64, 6, v_patch_nums=pn).state_dict())
+    assert kl == {"ema_vocab_hit_SV", "scaler"} | {f"quant_resi.qresi_ls.{i}.{n}" for i in range(4)
+                                                    for n in ("weight", "bias")}
+    q = VectorQuantizer2(64, 8, v_patch_nums=[1, 1, 2, 3, 3, 4, 5, 6, 8, 11])
+    assert q._phi_map(10) == [0, 0, 1, 1, 1, 2, 2, 3, 3, 3]        # SURVEY.md 8a / quant.py:285-288
+    assert VectorQuantizer2(8, 4, v_patch_nums=pn, share_quant_resi=1)._phi_map(3) == [0, 0, 0]
+    assert VectorQuantizer2(8, 4, v_patch_nums=pn, share_quant_resi=0)._phi_map(3) == [0, 1, 2]
