@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- tokenizer training throughput (images/sec at 256x256) + VQ-argmin roofline.
+
+    python bench.py --gpus 1 --steps 8 --warmup 3                    # our arm (CUDA path)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # CPU arm: the oracle port
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ... # one rank per GPU (NCCL)
+
+Workload (BASELINE.json configs[1]): VQ-8192 tokenizer training, bf16 autocast, per-GPU batch 256,
+256x256 synthetic images, random-init ViT-B encoder/decoder.  One step = VQModel forward
+(encode -> quantize -> latent perturbation -> decode) + L2 reconstruction/vq/commit losses + backward
++ AdamW (+ DDP gradient all-reduce for N > 1): the body of xqgan_train.py:448-462 restricted to the
+in-scope path (no LPIPS / discriminator / frozen teacher, whose weights cannot be downloaded here --
+BASELINE.md section 3).  Weak scaling: per-GPU batch is fixed.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "VQ-8192"
+METRIC = "tokenizer_train_images_per_sec_256x256"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=6)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", type=str, default=WORKLOAD)
+    p.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline step (0 = auto)")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+def build_model(workload: str, device):
+    from imagefolder_b200 import config as xcfg
+    cfg = dict(xcfg.SHIPPED_CONFIGS[workload])
+    cfg.update(semantic_guide="none", detail_guide="none")  # teachers need downloaded weights (out of scope)
+    args = xcfg.parse_args([])
+    for k, v in cfg.items():
+        setattr(args, k, v)
+    torch.manual_seed(0)
+    model = xcfg.build_vq_model(args)
+    return model.to(device), args
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from imagefolder_b200 import _capi, config as xcfg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True   # xqgan_train.py:5-6
+    torch.backends.cudnn.allow_tf32 = True
+
+    model, margs = build_model(a.workload, dev)
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+    B = a.batch
+    g = torch.Generator(device=dev).manual_seed(1234 * world + rank)
+    imgs_dev = torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1
+    imgs_host = imgs_dev.cpu().pin_memory()
+    alpha, beta, delta = xcfg.perturbation_schedule(margs, 0)
+
+    def step(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            dec, (vq, commit, ent, usages), _, _, _ = net(x, 0, alpha, beta, delta)
+            loss = F.mse_loss(dec.float(), x) + vq + commit + ent
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(imgs_dev)
+    barrier()
+    torch.cuda.reset_peak_memory_stats()
+
+    # ---- timed region 1: inputs resident in HBM
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _capi.TIMING = {}
+    _capi.LAUNCHES[0] = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step(imgs_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _capi.LAUNCHES[0]
+    timing = _capi.TIMING
+    _capi.TIMING = None
+    kern_ms = None
+    if "xq_vq_forward" in timing:
+        ts = [s.elapsed_time(e) for s, e in timing["xq_vq_forward"]]
+        kern_ms = sum(ts) / len(ts)
+    elif "xq_ms_forward" in timing:
+        ts = [s.elapsed_time(e) for s, e in timing["xq_ms_forward"]]
+        kern_ms = sum(ts) / len(ts)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        x = imgs_host.to(dev, non_blocking=True)       # H2D of this step's inputs (pinned)
+        loss = step(x)
+        loss_host = float(loss.detach())                # D2H read of the step's result
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf, src = peaks()
+    q = model.quantizes[0] if model.product_quant > 1 else model.quantize
+    C, V = margs.codebook_embed_dim, margs.codebook_size
+    rows = B * (margs.num_latent_tokens if len(margs.v_patch_nums) == 1 else sum(p * p for p in margs.v_patch_nums))
+    bytes_alg = rows * C * 4 + V * C * 4 + rows * 8 + rows * C * 4     # z + codebook + int64 idx + z_q
+    flops_alg = 2.0 * rows * V * C
+    roof = None
+    if kern_ms:
+        ach = bytes_alg / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "vq_search_kernel (xq_vq_forward call: prep + search + finalize)",
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": src, "kernel_ms": kern_ms, "algorithmic_bytes": bytes_alg,
+                "contraction_tflops": flops_alg / (kern_ms * 1e-3) / 1e12,
+                "note": "exact-fp32 CUDA-core search: FMA-pipe bound, not HBM bound (DESIGN.md section 5)"}
+    out = {
+        "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{a.workload} tokenizer training step, per-GPU batch {B}, 256x256, ViT-B enc/dec, "
+                               "fwd+bwd+AdamW, L2+vq+commit loss (no LPIPS/GAN/teacher)",
+                   "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2_policy": "inputs (201 MB/step) + activations exceed the 126 MB L2"},
+        "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": imgs_host.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "peak_mem_gib": peak_mem,
+        "last_loss": loss_host,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_arm(a, steps=1, warmup=0, state=model.state_dict(), margs=model.config)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_arm(a, steps, warmup, state=None, margs=None):
+    """the oracle port of the same training step on the host cores (bounded sample)."""
+    from oracle import vit_ref, xq_oracle as xo
+    import torch.nn.functional as F  # noqa: F401
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    xo.set_num_threads(cores)
+    if state is None:
+        model, _ = build_model(a.workload, "cpu")
+        state, margs = model.state_dict(), model.config
+    cfg = vit_ref.cfg_from_model_args(margs)
+    ref = vit_ref.RefTokenizer(state, cfg, requires_grad=True)
+    opt = torch.optim.AdamW(ref.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.0)
+    n = a.cpu_sample
+    g = torch.Generator().manual_seed(7)
+    SN = len(cfg["v_patch_nums"])
+    if n <= 0:  # size the sample for ~10-20 s per step
+        x = torch.rand(2, 3, 256, 256, generator=g) * 2 - 1
+        t0 = time.time()
+        ref.train_step(x, opt, dropout=torch.randint(3, SN + 1, (2,)).numpy() if SN > 1 else None)
+        per_img = (time.time() - t0) / 2
+        n = int(max(2, min(64, 12.0 / max(per_img, 1e-3))))
+    x = torch.rand(n, 3, 256, 256, generator=g) * 2 - 1
+    dr = torch.randint(3, SN + 1, (n,)).numpy() if SN > 1 else None
+    for _ in range(warmup):
+        ref.train_step(x, opt, dr)
+    t0 = time.time()
+    for _ in range(steps):
+        ref.train_step(x, opt, dr)
+    dt = time.time() - t0
+    return {"value": n * steps / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} images/step x {steps} step(s) of the {a.workload} training step (fp32, torch CPU ViT + "
+                      f"C oracle quantizer), {dt:.1f} s", "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_arm(a, steps=max(1, a.steps), warmup=min(a.warmup, 1))
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
+           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": base["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{a.workload} tokenizer training step on host cores (oracle port of the reference "
+                                  "path; the reference itself is Python + un-vendored timm and cannot travel)"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -89,6 +89,26 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+# --- instrumentation used by bench.py (off by default) ---------------------------------------
+TIMING = None        # dict name -> [(start_event, end_event), ...] when enabled
+LAUNCHES = [0]       # number of libxqb200 kernels launched (counted per C call)
+
+
+def call(name: str, n_kernels: int, fn, *args) -> None:
+    """invoke a C-ABI entry point, map its return code, count its kernel launches and (when
+    TIMING is enabled) bracket it with CUDA events on the current stream."""
+    LAUNCHES[0] += n_kernels
+    if TIMING is None:
+        check(fn(*args), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    TIMING.setdefault(name, []).append((s, e))
+    check(rc, name)
+
+
 def check(rc: int, what: str) -> None:
     if rc == 0:
         return

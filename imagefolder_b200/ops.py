@@ -38,9 +38,8 @@ class _VQForward(torch.autograd.Function):
         hist = torch.zeros(V, dtype=torch.float32, device=dev) if want_hist else None
         L = C.lib()
         ws = C.workspace(L.xq_vq_workspace_bytes(B, Cc, HW, V), dev)
-        C.check(L.xq_vq_forward(C.ptr(z), C.ptr(E), B, Cc, HW, V, int(codebook_norm), 1, float(beta), C.ptr(idx),
-                                C.ptr(out), C.ptr(loss), C.ptr(hist), C.ptr(ws), ws.numel(), C.stream_ptr(dev)),
-                "xq_vq_forward")
+        C.call("xq_vq_forward", 3, L.xq_vq_forward, C.ptr(z), C.ptr(E), B, Cc, HW, V, int(codebook_norm), 1,
+               float(beta), C.ptr(idx), C.ptr(out), C.ptr(loss), C.ptr(hist), C.ptr(ws), ws.numel(), C.stream_ptr(dev))
         ctx.save_for_backward(z, E, idx)
         ctx.beta, ctx.codebook_norm = float(beta), bool(codebook_norm)
         ctx.mark_non_differentiable(idx)
@@ -60,9 +59,9 @@ class _VQForward(torch.autograd.Function):
         gz = torch.empty_like(z)
         gE = torch.empty_like(E)
         L = C.lib()
-        C.check(L.xq_vq_backward(C.ptr(z), C.ptr(E), C.ptr(idx), C.ptr(g_out), C.ptr(g_vq), C.ptr(g_commit), B, Cc, HW,
-                                 V, int(ctx.codebook_norm), ctx.beta, C.ptr(gz), C.ptr(gE), C.stream_ptr(z.device)),
-                "xq_vq_backward")
+        C.call("xq_vq_backward", 1, L.xq_vq_backward, C.ptr(z), C.ptr(E), C.ptr(idx), C.ptr(g_out), C.ptr(g_vq),
+               C.ptr(g_commit), B, Cc, HW, V, int(ctx.codebook_norm), ctx.beta, C.ptr(gz), C.ptr(gE),
+               C.stream_ptr(z.device))
         return gz, gE, None, None, None
 
 
@@ -82,8 +81,8 @@ def vq_lookup(z, E, codebook_norm=True) -> Tuple[torch.Tensor, torch.Tensor]:
     out = torch.empty_like(z)
     L = C.lib()
     ws = C.workspace(L.xq_vq_workspace_bytes(B, Cc, HW, V), dev)
-    C.check(L.xq_vq_forward(C.ptr(z), C.ptr(E), B, Cc, HW, V, int(codebook_norm), 0, 0.0, C.ptr(idx), C.ptr(out),
-                            None, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev)), "xq_vq_forward")
+    C.call("xq_vq_lookup", 2, L.xq_vq_forward, C.ptr(z), C.ptr(E), B, Cc, HW, V, int(codebook_norm), 0, 0.0,
+           C.ptr(idx), C.ptr(out), None, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
     return out, idx
 
 
@@ -103,9 +102,10 @@ class _Perturb(torch.autograd.Function):
         ws = C.workspace(L.xq_perturb_workspace_bytes(B, Cc, HW, V), dev)
         ru = rand_u.float().contiguous() if rand_u is not None else None
         rj = rand_j.to(torch.int64).contiguous() if rand_j is not None else None
-        C.check(L.xq_perturb_forward(C.ptr(z), C.ptr(z_q), C.ptr(E), C.ptr(ru), C.ptr(rj), B, Cc, HW, V,
-                                     int(codebook_norm), float(alpha), int(n_perturb), int(delta), C.ptr(out), None,
-                                     C.ptr(ws), ws.numel(), C.stream_ptr(dev)), "xq_perturb_forward")
+        nk = (1 if n_perturb < B else 0) + (2 if n_perturb > 0 else 0)
+        C.call("xq_perturb_forward", nk, L.xq_perturb_forward, C.ptr(z), C.ptr(z_q), C.ptr(E), C.ptr(ru), C.ptr(rj),
+               B, Cc, HW, V, int(codebook_norm), float(alpha), int(n_perturb), int(delta), C.ptr(out), None,
+               C.ptr(ws), ws.numel(), C.stream_ptr(dev))
         ctx.save_for_backward(z)
         ctx.codebook_norm, ctx.n_perturb = bool(codebook_norm), int(n_perturb)
         return out
@@ -119,8 +119,8 @@ class _Perturb(torch.autograd.Function):
         gz = torch.empty_like(z)
         gzq = torch.empty_like(z)
         L = C.lib()
-        C.check(L.xq_perturb_backward(C.ptr(z), C.ptr(g), B, Cc, HW, int(ctx.codebook_norm), ctx.n_perturb, C.ptr(gz),
-                                      C.ptr(gzq), C.stream_ptr(z.device)), "xq_perturb_backward")
+        C.call("xq_perturb_backward", 1, L.xq_perturb_backward, C.ptr(z), C.ptr(g), B, Cc, HW,
+               int(ctx.codebook_norm), ctx.n_perturb, C.ptr(gz), C.ptr(gzq), C.stream_ptr(z.device))
         return gz, gzq, None, None, None, None, None, None, None
 
 
@@ -152,9 +152,10 @@ class _MSForward(torch.autograd.Function):
         hist = torch.zeros(desc.SN, desc.V, dtype=torch.float32, device=dev) if want_hist else None
         saved = C.workspace(L.xq_ms_saved_bytes(desc), dev)
         ws = C.workspace(L.xq_ms_workspace_bytes(desc), dev)
-        C.check(L.xq_ms_forward(desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), C.ptr(nq), 1, C.ptr(out),
-                                C.ptr(idx_all), None, C.ptr(loss), C.ptr(hist), C.ptr(saved), C.ptr(ws), ws.numel(),
-                                C.stream_ptr(dev)), "xq_ms_forward")
+        nk = 2 + (1 if desc.channel_norm else 0) + (1 if E is not None else 1)
+        C.call("xq_ms_forward", nk, L.xq_ms_forward, desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), C.ptr(nq), 1,
+               C.ptr(out), C.ptr(idx_all), None, C.ptr(loss), C.ptr(hist), C.ptr(saved), C.ptr(ws), ws.numel(),
+               C.stream_ptr(dev))
         ctx.desc = desc
         ctx.has = (E is not None, phi_w is not None)
         ctx.save_for_backward(f, E, phi_w, phi_b, nq, idx_all, saved)
@@ -178,10 +179,10 @@ class _MSForward(torch.autograd.Function):
         gw = torch.empty_like(phi_w) if phi_w is not None else None
         gb = torch.empty_like(phi_b) if phi_b is not None else None
         ws = C.workspace(L.xq_ms_workspace_bytes(desc), dev)
-        C.check(L.xq_ms_backward(desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), C.ptr(nq), C.ptr(idx_all),
-                                 C.ptr(saved), C.ptr(g_out), C.ptr(g_vq), C.ptr(g_commit), C.ptr(g_ent), C.ptr(gf),
-                                 C.ptr(gE), C.ptr(gw), C.ptr(gb), C.ptr(ws), ws.numel(), C.stream_ptr(dev)),
-                "xq_ms_backward")
+        nk = 1 + (2 if phi_w is not None else 0) + (1 if (E is None and g_ent is not None) else 0)
+        C.call("xq_ms_backward", nk, L.xq_ms_backward, desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), C.ptr(nq),
+               C.ptr(idx_all), C.ptr(saved), C.ptr(g_out), C.ptr(g_vq), C.ptr(g_commit), C.ptr(g_ent), C.ptr(gf),
+               C.ptr(gE), C.ptr(gw), C.ptr(gb), C.ptr(ws), ws.numel(), C.stream_ptr(dev))
         return gf, gE, gw, gb, None, None, None
 
 
@@ -214,8 +215,9 @@ def ms_lookup(f, E, phi_w, phi_b, desc, want_fhat_scales: bool):
     out = torch.empty_like(f)
     fs = torch.empty((desc.SN,) + tuple(f.shape), dtype=torch.float32, device=dev) if want_fhat_scales else None
     ws = C.workspace(L.xq_ms_workspace_bytes(desc), dev)
-    C.check(L.xq_ms_forward(desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), None, 0, C.ptr(out), C.ptr(idx_all),
-                            C.ptr(fs), None, None, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev)), "xq_ms_forward")
+    nk = 1 + (1 if desc.channel_norm else 0) + (1 if E is not None else 0)
+    C.call("xq_ms_lookup", nk, L.xq_ms_forward, desc, C.ptr(f), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), None, 0,
+           C.ptr(out), C.ptr(idx_all), C.ptr(fs), None, None, None, C.ptr(ws), ws.numel(), C.stream_ptr(dev))
     return out, idx_all, fs
 
 
@@ -232,8 +234,8 @@ def ms_decode(idx_all, E, phi_w, phi_b, desc, want_out=True, want_fhat_scales=Fa
     Lv = sum(int(desc.patch_nums[i]) ** 2 for i in range(1, desc.SN))
     var = torch.empty(desc.B, Lv, desc.C, dtype=torch.float32, device=dev) if (want_var_input and Lv > 0) else None
     L = C.lib()
-    C.check(L.xq_ms_decode(desc, C.ptr(idx_all.contiguous()), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b), C.ptr(out),
-                           C.ptr(fs), C.ptr(var), C.stream_ptr(dev)), "xq_ms_decode")
+    C.call("xq_ms_decode", 1, L.xq_ms_decode, desc, C.ptr(idx_all.contiguous()), C.ptr(E), C.ptr(phi_w), C.ptr(phi_b),
+           C.ptr(out), C.ptr(fs), C.ptr(var), C.stream_ptr(dev))
     return out, fs, var
 
 
@@ -243,6 +245,6 @@ def usage_ema_(ema: torch.Tensor, hit: torch.Tensor, record_hit: int, margin: fl
     V = ema.shape[-1]
     usage = torch.empty(rows, dtype=torch.float32, device=ema.device)
     L = C.lib()
-    C.check(L.xq_usage_ema(C.ptr(ema), C.ptr(hit.contiguous()), rows, V, int(record_hit), float(margin), C.ptr(usage),
-                           C.stream_ptr(ema.device)), "xq_usage_ema")
+    C.call("xq_usage_ema", 1, L.xq_usage_ema, C.ptr(ema), C.ptr(hit.contiguous()), rows, V, int(record_hit),
+           float(margin), C.ptr(usage), C.stream_ptr(ema.device))
     return usage

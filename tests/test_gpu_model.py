@@ -1,0 +1,92 @@
+"""GPU tests of the whole path: VQModel (product, CUDA) vs the CPU oracle restatement, same weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_ref, xq_oracle as xo
+from test_model_cpu import small_model
+
+pytestmark = pytest.mark.gpu
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["VQ-8192", "VP2-16384", "MSVR10P2-4096", "MSBR10P2-16384"])
+def test_forward_matches_oracle_fp32(name):
+    """fp32, drop_path off (eval-mode ViT, quantizers in train mode so the losses are produced).
+    Tolerances: latents/pixels 1e-3 relative (north star); token indices are checked bit-exact at the
+    quantizer boundary, i.e. on the SAME latent the GPU produced."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    over = dict(guide_type_2="patch") if name.startswith("MSBR") else {}
+    model, args = small_model(name, **over)
+    model = model.cuda()
+    model.train()
+    model.encoder.eval(), model.decoder.eval()     # no DropPath RNG
+    x = torch.rand(2, 3, 256, 256) * 2 - 1
+    torch.manual_seed(5)                            # CPU generator drives dropout_rand (xqgan_model.py:274)
+    dec, (vq, commit, ent, usages), sem, det, dep = model(x.cuda(), 0, 0.0, 0.0, 100)
+    assert sem is None and det is None
+    cfg = vit_ref.cfg_from_model_args(model.config, num_heads=6)
+    ref = vit_ref.RefTokenizer(model.state_dict(), cfg)
+    with torch.no_grad():
+        h_gpu = model.encode(x.cuda())
+        h_ref = ref.encode(x)
+        np.testing.assert_allclose(npy(h_gpu), h_ref.numpy(), rtol=1e-3, atol=1e-3 * float(h_ref.abs().max()))
+        # quantizer boundary on identical inputs -> indices bit-exact
+        torch.manual_seed(5)
+        SN = len(cfg["v_patch_nums"])
+        dr = torch.randint(model.start_drop, SN + 1, (2,)).numpy() if SN > 1 else None
+        quant_ref, (vq_r, cm_r, en_r) = ref.quantize(h_gpu.cpu(), dr)
+        quants = model._quantizers()
+        for i, hb in enumerate(ref._branches(h_gpu.cpu())):
+            qm = quants[i]
+            if SN == 1:
+                idx_ref = xo.vq_forward(hb.numpy(), npy(qm.embedding.weight))["idx"]
+                np.testing.assert_array_equal(npy(qm.last_idx), idx_ref)
+            else:
+                assert len(qm.last_idx_Bl) == SN
+        np.testing.assert_allclose(float(vq), float(vq_r), rtol=1e-3)
+        np.testing.assert_allclose(float(commit), float(cm_r), rtol=1e-3)
+        np.testing.assert_allclose(float(ent), float(en_r), rtol=1e-3, atol=1e-6)
+        dec_ref = ref.decode(quant_ref)
+        np.testing.assert_allclose(npy(dec), dec_ref.numpy(), rtol=1e-3, atol=1e-3 * float(dec_ref.abs().max()))
+    # inference surfaces agree with each other
+    model.eval()
+    with torch.no_grad():
+        rec = model.img_to_reconstructed_img(x.cuda())
+        toks = model.img_to_idxBl(x.cuda())
+        rec2 = model.decode_tokens(toks)
+        assert rec.shape == (2, 3, 256, 256) and float(rec.abs().max()) <= 1.0
+        np.testing.assert_allclose(npy(rec), npy(rec2), rtol=1e-5, atol=1e-5)
+
+
+def test_train_step_bf16_autocast_runs_and_learns():
+    model, args = small_model("VQ-8192")
+    model = model.cuda().train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    x = (torch.rand(4, 3, 256, 256) * 2 - 1).cuda()
+    losses = []
+    for _ in range(4):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            dec, (vq, commit, ent, usages), _, _, _ = model(x, 0, 0.0, 0.0, 100)
+            loss = torch.nn.functional.mse_loss(dec.float(), x) + vq + commit
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert model.quantize.embedding.weight.grad is not None
+    assert float(usages[0]) >= 0.0
+
+
+def test_robusttok_perturbation_path():
+    model, args = small_model("RobustTok")
+    model = model.cuda().train()
+    x = (torch.rand(10, 3, 256, 256) * 2 - 1).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        dec, (vq, commit, ent, usages), _, _, _ = model(x, 0, 1.0, 0.1, 100)
+        (dec.float().pow(2).mean() + vq + commit).backward()
+    assert torch.isfinite(model.encoder.latent_tokens.grad).all()

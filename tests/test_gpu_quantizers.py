@@ -336,8 +336,11 @@ def test_msvr_full_size_properties():
     # residual energy decreases with scale
     errs = [float((fh[si] - f).pow(2).mean()) for si in range(len(pn))]
     assert errs[-1] < errs[0]
-    # STE value equals the last cumulative f_hat up to fp32 rounding of (F - f) + f
-    assert float((out - fh[-1]).abs().max()) < 1e-5
+    # STE value equals the last cumulative f_hat up to fp32 rounding of (F - f) + f -- for the samples
+    # without quantizer dropout (the first int(B*codebook_drop) samples lose their late scales)
+    nd = int(128 * 0.1)
+    assert float((out[nd:] - fh[-1][nd:]).abs().max()) < 1e-5
+    assert float((out[:nd] - fh[-1][:nd]).abs().max()) > 1e-3
     # oracle on 2 images
     mods = q.quant_resi.modules_list()
     fwd = xo.vq2_f_to_idxBl_or_fhat(npy(f[:2]), npy(q.embedding.weight), np.stack([npy(m.weight) for m in mods]),
