@@ -12,6 +12,7 @@ import math
 import torch
 import torch.nn as nn
 
+from ..vit_ops import run_blocks
 from .to_pixel import ToPixel
 from .vision_transformer import Attention, create_model, trunc_normal_
 
@@ -115,14 +116,8 @@ class DINOv2Encoder(nn.Module):
                         x += self.lvl_embed(self.lvl1LC.expand(x.size(0), -1))
                 else:
                     x = torch.cat([x, z + self.latent_pos_embed], dim=1)
-        x = x.to(_main_dtype(x))
-        x = self.model.norm_pre(x)
-        if self.use_attn_mask:
-            for blk in self.model.blocks:
-                x = blk(x, self.attn_mask)
-        else:
-            x = self.model.blocks(x)
-        x = self.model.norm(x)
+        # norm_pre -> blocks -> norm (dinov2.py:176-190); fused CUDA glue under bf16 autocast
+        x = run_blocks(self.model, x, self.attn_mask if self.use_attn_mask else None)
         if self.num_latent_tokens:
             return x[:, -self.num_latent_tokens:]
         return x[:, self.num_prefix_tokens:]
@@ -207,9 +202,6 @@ class DINOv2Decoder(nn.Module):
             x = torch.cat([x, z], dim=1)
             if self.abs_pos_embed:
                 x += self.lvl_embed(self.lvl1LC.expand(x.size(0), -1))
-        x = x.to(_main_dtype(x))
-        x = self.model.norm_pre(x)
-        x = self.model.blocks(x)
-        x = self.model.norm(x)
+        x = run_blocks(self.model, x)
         x = x[:, self.num_prefix_tokens:self.num_img_tokens + self.num_prefix_tokens]
         return self.to_pixel(x)

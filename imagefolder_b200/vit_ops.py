@@ -1,0 +1,150 @@
+"""Fused ViT block glue over libxqb200 (csrc/vit_kernels.cu).
+
+`run_blocks(vit, x)` walks `vit.blocks` + `vit.norm` exactly like the reference
+(dino_enc/dinov2.py:183-190 -> vision_transformer.py:336-339) but replaces every chain
+   [+ residual] -> LayerScale -> DropPath -> add -> LayerNorm -> cast-to-bf16
+by ONE kernel (`xq_vit_residual_ln_fwd`) and GELU by one bf16 kernel; GEMMs stay on cuBLAS and
+attention on the SDPA library kernel.  The residual stream is fp32 and the GEMM operands bf16,
+which is what bf16 autocast gives the reference, so the numerics are the reference's.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi as C
+
+_SUPPORTED_D = (384, 768, 1024)
+
+
+class _ResidualLN(torch.autograd.Function):
+    """(x, branch, ls_gamma, rowscale, ln_w, ln_b) -> (x_out fp32, y bf16)."""
+
+    @staticmethod
+    def forward(ctx, x, branch, ls_gamma, rowscale, ln_w, ln_b, eps: float):
+        Bn, S, D = x.shape
+        M = Bn * S
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        if branch is not None:
+            branch = branch.contiguous()
+            if branch.dtype != torch.bfloat16:
+                branch = branch.to(torch.bfloat16)
+        x_out = torch.empty_like(x)
+        y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        L = C.lib()
+        C.call("xq_vit_residual_ln_fwd", 1, L.xq_vit_residual_ln_fwd, C.ptr(x), C.ptr(branch), C.ptr(ls_gamma),
+               C.ptr(rowscale), S, C.ptr(ln_w), C.ptr(ln_b), float(eps), M, D, C.ptr(x_out), C.ptr(y), C.ptr(mean),
+               C.ptr(rstd), C.stream_ptr(x.device))
+        ctx.save_for_backward(x_out, mean, rstd, ln_w, branch, ls_gamma, rowscale)
+        ctx.shape = (Bn, S, D)
+        ctx.set_materialize_grads(False)
+        return x_out, y
+
+    @staticmethod
+    def backward(ctx, g_xout, g_y):
+        x_out, mean, rstd, ln_w, branch, ls_gamma, rowscale = ctx.saved_tensors
+        Bn, S, D = ctx.shape
+        M = Bn * S
+        dev = x_out.device
+        if g_xout is not None:
+            g_xout = g_xout.contiguous()
+            if g_xout.dtype != torch.float32:
+                g_xout = g_xout.float()
+        if g_y is not None:
+            g_y = g_y.contiguous()
+            if g_y.dtype != torch.bfloat16:
+                g_y = g_y.to(torch.bfloat16)
+        g_x = torch.empty_like(x_out)
+        g_branch = torch.empty_like(branch) if branch is not None else None
+        g_w = torch.empty_like(ln_w)
+        g_b = torch.empty_like(ln_w)
+        g_g = torch.empty_like(ls_gamma) if (branch is not None and ls_gamma is not None) else None
+        L = C.lib()
+        ws = C.workspace(L.xq_vit_ln_bwd_workspace_bytes(D), dev)
+        C.call("xq_vit_residual_ln_bwd", 2, L.xq_vit_residual_ln_bwd, C.ptr(g_xout), C.ptr(g_y), C.ptr(x_out),
+               C.ptr(mean), C.ptr(rstd), C.ptr(ln_w), C.ptr(branch), C.ptr(ls_gamma), C.ptr(rowscale), S, M, D,
+               C.ptr(g_x), C.ptr(g_branch), C.ptr(g_w), C.ptr(g_b), C.ptr(g_g), C.ptr(ws), ws.numel(),
+               C.stream_ptr(dev))
+        return g_x, g_branch, g_g, None, g_w, g_b, None
+
+
+def residual_ln(x, branch, ls_gamma, rowscale, ln_w, ln_b, eps=1e-6):
+    return _ResidualLN.apply(x, branch, ls_gamma, rowscale, ln_w, ln_b, eps)
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L = C.lib()
+        C.call("xq_vit_gelu_fwd", 1, L.xq_vit_gelu_fwd, C.ptr(x), C.ptr(y), x.numel(), C.stream_ptr(x.device))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        if gy.dtype != torch.bfloat16:
+            gy = gy.to(torch.bfloat16)
+        gx = torch.empty_like(x)
+        L = C.lib()
+        C.call("xq_vit_gelu_bwd", 1, L.xq_vit_gelu_bwd, C.ptr(x), C.ptr(gy), C.ptr(gx), x.numel(), C.stream_ptr(x.device))
+        return gx
+
+
+def gelu_bf16(x):
+    return _Gelu.apply(x)
+
+
+def _droppath_scale(mod, batch: int, device):
+    """DropPath (timm): per-sample keep mask / keep_prob, or None when inactive."""
+    p = getattr(mod, "drop_prob", 0.0)
+    if p == 0.0 or not mod.training:
+        return None
+    keep = 1.0 - p
+    t = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
+    if keep > 0.0 and getattr(mod, "scale_by_keep", True):
+        t.div_(keep)
+    return t
+
+
+def fused_path_ok(vit, x) -> bool:
+    return (x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and vit.embed_dim in _SUPPORTED_D and isinstance(vit.norm_pre, nn.Identity))
+
+
+def run_blocks(vit, x, attn_mask=None):
+    """x: [B,S,D] token stream after pos-embed (fp32).  Returns norm(blocks(x)) as bf16 on the fused
+    path, or the plain module path result otherwise (fp32 parity runs, CPU)."""
+    if attn_mask is not None or not fused_path_ok(vit, x):
+        x = x.to(torch.matmul(x.new_ones(8, 8), x.new_ones(8, 8)).dtype)   # dinov2.py:177-179
+        x = vit.norm_pre(x)
+        if attn_mask is not None:
+            for blk in vit.blocks:
+                x = blk(x, attn_mask)
+        else:
+            x = vit.blocks(x)
+        return vit.norm(x)
+    Bn = x.shape[0]
+    dev = x.device
+    x = x.float()
+    branch = gamma = rs = None
+    for blk in vit.blocks:
+        x, y = residual_ln(x, branch, gamma, rs, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+        a = blk.attn(y)
+        g1 = blk.ls1.gamma if hasattr(blk.ls1, "gamma") else None
+        x, y = residual_ln(x, a, g1, _droppath_scale(blk.drop_path1, Bn, dev), blk.norm2.weight, blk.norm2.bias,
+                           blk.norm2.eps)
+        h = gelu_bf16(blk.mlp.fc1(y))
+        branch = blk.mlp.fc2(h)
+        gamma = blk.ls2.gamma if hasattr(blk.ls2, "gamma") else None
+        rs = _droppath_scale(blk.drop_path2, Bn, dev)
+    _, y = residual_ln(x, branch, gamma, rs, vit.norm.weight, vit.norm.bias, vit.norm.eps)
+    return y

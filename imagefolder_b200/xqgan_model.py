@@ -24,6 +24,7 @@ from typing import List
 
 import torch
 import torch.distributed as tdist
+import torch.distributed.nn  # noqa: F401  (differentiable all_gather)
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -118,7 +119,6 @@ class ClipLoss(nn.Module):
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if self.world_size > 1:
-            import torch.distributed.nn
             if self.gather_with_grad:
                 all_i = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
                 all_t = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)

@@ -171,6 +171,31 @@ int xq_ms_decode(const xq_ms_desc *d, const int64_t *idx_all, const float *E, co
 int xq_usage_ema(float *ema, const float *hit, int rows, int V, int record_hit, float margin,
                  float *usage_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ViT block glue (DINOv2Encoder / DINOv2Decoder blocks)
+ *   replaces the non-GEMM ops of Block.forward   tokenizer/tokenizer_image/dino_enc/vision_transformer.py:336-339
+ *   (LayerNorm :301,316 ; LayerScale :280-292 ; DropPath ; residual add) and Mlp's GELU.
+ * Residual stream fp32 [M,D], GEMM operands bf16 (what bf16 autocast gives the reference).
+ * D in {384, 768, 1024}.  `branch`, `y`, `g_y`, `g_branch` are bf16 [M,D].
+ * ------------------------------------------------------------------------------------------ */
+/*   x_out = x + rowscale[row / rows_per_sample] * ls_gamma[d] * branch   (branch may be NULL: x_out = x)
+ *   y     = LayerNorm(x_out; eps) * ln_w + ln_b   (bf16; may be NULL)   mean / rstd [M] saved for backward
+ *   rowscale [B] = DropPath keep mask / keep_prob (NULL = 1);  x_out may alias x or be NULL */
+int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *ls_gamma, const float *rowscale,
+                           int rows_per_sample, const float *ln_w, const float *ln_b, float eps, int M, int D,
+                           float *x_out, void *y, float *mean, float *rstd, void *stream);
+size_t xq_vit_ln_bwd_workspace_bytes(int D);
+/*   G = g_xout + LayerNorm^T(g_y)  -> g_x [M,D] fp32 ; g_branch = G * rowscale * ls_gamma (bf16)
+ *   g_ln_w, g_ln_b, g_ls_gamma [D] overwritten (any may be NULL) */
+int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_out, const float *mean,
+                           const float *rstd, const float *ln_w, const void *branch, const float *ls_gamma,
+                           const float *rowscale, int rows_per_sample, int M, int D, float *g_x, void *g_branch,
+                           float *g_ln_w, float *g_ln_b, float *g_ls_gamma, void *workspace,
+                           size_t workspace_bytes, void *stream);
+/*   exact (erf) GELU on bf16, n % 8 == 0 (timm Mlp act_layer=nn.GELU) */
+int xq_vit_gelu_fwd(const void *x, void *y, size_t n, void *stream);
+int xq_vit_gelu_bwd(const void *x, const void *gy, void *gx, size_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

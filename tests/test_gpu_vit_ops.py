@@ -1,0 +1,111 @@
+"""Numerics of the ViT glue kernels against a plain PyTorch fp32 reference of the same op
+(floating-point kernels: tolerance set by the bf16 operands, written per assertion)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_residual_ln(x, branch, gamma, rs, w, b, eps, S):
+    x = x.double()
+    if branch is not None:
+        s = rs.double().repeat_interleave(S).view(x.shape[0], x.shape[1], 1) if rs is not None else 1.0
+        g = gamma.double() if gamma is not None else 1.0
+        x = x + s * g * branch.double()
+    y = F.layer_norm(x, (x.shape[-1],), w.double(), b.double(), eps)
+    return x, y
+
+
+@pytest.mark.parametrize("D,Bn,S", [(768, 3, 37), (384, 2, 513), (1024, 1, 9)])
+@pytest.mark.parametrize("with_branch", [True, False])
+def test_residual_ln_fwd_bwd(D, Bn, S, with_branch):
+    from imagefolder_b200.vit_ops import residual_ln
+    torch.manual_seed(D + S)
+    dev = "cuda"
+    x = torch.randn(Bn, S, D, device=dev, requires_grad=True)
+    branch = (torch.randn(Bn, S, D, device=dev) * 2).to(torch.bfloat16).requires_grad_(True) if with_branch else None
+    gamma = (torch.rand(D, device=dev) + 0.5).requires_grad_(True) if with_branch else None
+    rs = torch.tensor([0.0, 1 / 0.9, 1 / 0.9][:Bn], device=dev) if with_branch else None
+    w = (torch.rand(D, device=dev) + 0.5).requires_grad_(True)
+    b = torch.randn(D, device=dev, requires_grad=True)
+    x_out, y = residual_ln(x, branch, gamma, rs, w, b, 1e-6)
+    assert x_out.dtype == torch.float32 and y.dtype == torch.bfloat16
+    xr, yr = ref_residual_ln(x.detach(), branch.detach() if with_branch else None, gamma, rs, w, b, 1e-6, S)
+    np.testing.assert_allclose(x_out.detach().cpu().numpy(), xr.float().cpu().numpy(), rtol=1e-6, atol=1e-6)
+    # y is rounded to bf16: 2^-8 relative
+    np.testing.assert_allclose(y.float().detach().cpu().numpy(), yr.detach().float().cpu().numpy(), rtol=8e-3, atol=8e-3)
+    g_xo = torch.randn_like(x_out)
+    g_y = torch.randn_like(y)
+    (x_out * g_xo).sum().add((y.float() * g_y.float()).sum()).backward()
+    # fp64 autograd reference
+    x2 = x.detach().double().requires_grad_(True)
+    br2 = branch.detach().double().requires_grad_(True) if with_branch else None
+    ga2 = gamma.detach().double().requires_grad_(True) if with_branch else None
+    w2, b2 = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    xo2, y2 = ref_residual_ln(x2, br2, ga2, rs, w2, b2, 1e-6, S)
+    (xo2 * g_xo.double()).sum().add((y2 * g_y.double()).sum()).backward()
+
+    def chk(a, r, rtol):
+        r = r.float().cpu().numpy()
+        np.testing.assert_allclose(a.float().cpu().numpy(), r, rtol=rtol, atol=rtol * float(np.abs(r).max()))
+    chk(x.grad, x2.grad, 1e-4)
+    chk(w.grad, w2.grad, 1e-4)
+    chk(b.grad, b2.grad, 1e-4)
+    if with_branch:
+        chk(branch.grad, br2.grad, 8e-3)       # bf16 output
+        chk(gamma.grad, ga2.grad, 1e-4)
+
+
+def test_residual_ln_none_grads():
+    """final norm: only y is used downstream -> g_xout is None."""
+    from imagefolder_b200.vit_ops import residual_ln
+    x = torch.randn(2, 5, 768, device="cuda", requires_grad=True)
+    w = torch.ones(768, device="cuda", requires_grad=True)
+    b = torch.zeros(768, device="cuda", requires_grad=True)
+    _, y = residual_ln(x, None, None, None, w, b, 1e-6)
+    y.float().pow(2).sum().backward()
+    x2 = x.detach().double().requires_grad_(True)
+    F.layer_norm(x2, (768,), w.detach().double(), b.detach().double(), 1e-6).pow(2).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.float().cpu().numpy(), rtol=2e-2, atol=2e-2 * float(x2.grad.abs().max()))
+
+
+def test_gelu_bf16():
+    from imagefolder_b200.vit_ops import gelu_bf16
+    x = (torch.randn(4, 33, 3072, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
+    y = gelu_bf16(x)
+    ref = F.gelu(x.detach().float())
+    np.testing.assert_allclose(y.float().detach().cpu().numpy(), ref.cpu().numpy(), rtol=8e-3, atol=1e-3)
+    g = torch.randn_like(y)
+    y.backward(g)
+    x2 = x.detach().float().requires_grad_(True)
+    F.gelu(x2).backward(g.float())
+    np.testing.assert_allclose(x.grad.float().cpu().numpy(), x2.grad.cpu().numpy(), rtol=8e-3, atol=4e-3)
+
+
+def test_fused_blocks_match_module_path():
+    """bf16-autocast encoder through the fused glue == the plain module path (same weights, eval)."""
+    from imagefolder_b200.dino_enc import DINOv2Encoder
+    from imagefolder_b200 import vit_ops
+    kw = {'img_size': 256, 'patch_size': 16, 'drop_path_rate': 0.1}
+    torch.manual_seed(0)
+    enc = DINOv2Encoder(num_latent_tokens=256, model_name='vit_small_patch14_dinov2.lvd142m', model_kwargs=kw,
+                        tuning_method='full', abs_pos_embed=True).cuda().eval()
+    for blk in enc.model.blocks:            # make LayerScale matter
+        blk.ls1.gamma.data.fill_(0.5)
+        blk.ls2.gamma.data.fill_(0.5)
+    x = torch.rand(2, 3, 256, 256, device="cuda") * 2 - 1
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y_fused = enc(x)
+        orig = vit_ops.fused_path_ok
+        vit_ops.fused_path_ok = lambda *a, **k: False
+        try:
+            y_plain = enc(x)
+        finally:
+            vit_ops.fused_path_ok = orig
+    assert y_fused.dtype == torch.bfloat16
+    a, b = y_fused.float().cpu().numpy(), y_plain.float().cpu().numpy()
+    # both are bf16-GEMM pipelines; they differ only by rounding order
+    assert np.abs(a - b).max() < 0.06 * np.abs(b).max()
+    assert np.corrcoef(a.ravel(), b.ravel())[0, 1] > 0.9995
