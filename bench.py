@@ -242,7 +242,9 @@ def cpu_arm(a, steps, warmup, state=None, margs=None):
     """the oracle port of the same training step on the host cores (bounded sample)."""
     from oracle import vit_ref, xq_oracle as xo
     import torch.nn.functional as F  # noqa: F401
-    cores = os.cpu_count() or 1
+    # measured on the B200 host (128-core Xeon 8562Y+, tools/cpu_probe.py): 16 threads 1.10 img/s, 32 -> 1.05,
+    # 64 -> 0.53, 128 -> pathological (> 90 s/step): the step's small GEMMs do not scale past ~16-32 threads
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     xo.set_num_threads(cores)
     if state is None:
@@ -259,7 +261,7 @@ def cpu_arm(a, steps, warmup, state=None, margs=None):
         t0 = time.time()
         ref.train_step(x, opt, dropout=torch.randint(3, SN + 1, (2,)).numpy() if SN > 1 else None)
         per_img = (time.time() - t0) / 2
-        n = int(max(2, min(64, 12.0 / max(per_img, 1e-3))))
+        n = int(max(2, min(32, 12.0 / max(per_img, 1e-3))))
     x = torch.rand(n, 3, 256, 256, generator=g) * 2 - 1
     dr = torch.randint(3, SN + 1, (n,)).numpy() if SN > 1 else None
     for _ in range(warmup):

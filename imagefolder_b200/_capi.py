@@ -86,17 +86,19 @@ def lib() -> ctypes.CDLL:
     L.xq_usage_ema.restype = c_int
     L.xq_usage_ema.argtypes = [f32p, f32p, c_int, c_int, c_int, c_float, f32p, vp]
     L.xq_vit_residual_ln_fwd.restype = c_int
-    L.xq_vit_residual_ln_fwd.argtypes = [f32p, vp, f32p, f32p, c_int, f32p, f32p, c_float, c_int, c_int, f32p, vp, f32p,
-                                         f32p, vp]
+    L.xq_vit_residual_ln_fwd.argtypes = [f32p, vp, f32p, f32p, f32p, c_int, f32p, f32p, c_float, c_int, c_int, f32p, vp,
+                                         f32p, f32p, vp]
     L.xq_vit_ln_bwd_workspace_bytes.restype = c_size_t
     L.xq_vit_ln_bwd_workspace_bytes.argtypes = [c_int]
     L.xq_vit_residual_ln_bwd.restype = c_int
-    L.xq_vit_residual_ln_bwd.argtypes = [f32p, vp, f32p, f32p, f32p, f32p, vp, f32p, f32p, c_int, c_int, c_int, f32p, vp,
-                                         f32p, f32p, f32p, vp, c_size_t, vp]
+    L.xq_vit_residual_ln_bwd.argtypes = [f32p, vp, f32p, f32p, f32p, f32p, vp, f32p, f32p, f32p, c_int, c_int, c_int,
+                                         f32p, vp, f32p, f32p, f32p, f32p, vp, c_size_t, vp]
+    L.xq_vit_pack_qkv.restype = c_int
+    L.xq_vit_pack_qkv.argtypes = [vp, vp, vp, vp, c_size_t, c_int, vp]
     L.xq_vit_gelu_fwd.restype = c_int
-    L.xq_vit_gelu_fwd.argtypes = [vp, vp, c_size_t, vp]
+    L.xq_vit_gelu_fwd.argtypes = [vp, f32p, vp, c_int, c_int, vp]
     L.xq_vit_gelu_bwd.restype = c_int
-    L.xq_vit_gelu_bwd.argtypes = [vp, vp, vp, c_size_t, vp]
+    L.xq_vit_gelu_bwd.argtypes = [vp, f32p, vp, vp, f32p, c_int, c_int, vp]
     _lib = L
     return L
 
@@ -174,5 +176,5 @@ EXPORTED_SYMBOLS = [
     "xq_vq_backward", "xq_perturb_workspace_bytes", "xq_perturb_forward", "xq_perturb_backward",
     "xq_ms_workspace_bytes", "xq_ms_saved_bytes", "xq_ms_total_tokens", "xq_ms_forward", "xq_ms_backward",
     "xq_ms_decode", "xq_usage_ema", "xq_vit_residual_ln_fwd", "xq_vit_ln_bwd_workspace_bytes",
-    "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd",
+    "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd", "xq_vit_pack_qkv",
 ]

@@ -47,13 +47,14 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16 *p, float4 f) {
 }
 
 // One warp per row; NV = D / 128 float4 chunks per lane.
+//   x_new = x + rowscale * gamma_ls * (branch + branch_bias)
 template <int NV>
 __global__ void __launch_bounds__(THREADS)
 residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ branch,
-                       const float *__restrict__ ls_gamma, const float *__restrict__ rowscale, int rows_per_sample,
-                       const float *__restrict__ ln_w, const float *__restrict__ ln_b, float eps, int M,
-                       float *__restrict__ x_out, __nv_bfloat16 *__restrict__ y, float *__restrict__ mean_out,
-                       float *__restrict__ rstd_out) {
+                       const float *__restrict__ branch_bias, const float *__restrict__ ls_gamma,
+                       const float *__restrict__ rowscale, int rows_per_sample, const float *__restrict__ ln_w,
+                       const float *__restrict__ ln_b, float eps, int M, float *__restrict__ x_out,
+                       __nv_bfloat16 *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out) {
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -67,6 +68,10 @@ residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restr
         v[i] = *reinterpret_cast<const float4 *>(x + base + col);
         if (branch) {
             float4 b = load_bf16x4(branch + base + col);
+            if (branch_bias) {
+                float4 bb = *reinterpret_cast<const float4 *>(branch_bias + col);
+                b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+            }
             float4 g = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
             v[i].x += s * g.x * b.x; v[i].y += s * g.y * b.y; v[i].z += s * g.z * b.z; v[i].w += s * g.w * b.w;
         }
@@ -98,23 +103,27 @@ residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restr
     if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
-// Backward.  Persistent grid; each warp walks rows with stride, keeping its column partial sums in
-// registers; CTA partials -> part[blockIdx][3][D]; a second kernel reduces over blocks.
-//   g_xout may be null (no later residual gradient), g_y may be null (the LN output was unused).
+// Backward.  Persistent grid; each warp walks rows with a grid stride.  The four column partial sums
+// (d ln_w, d ln_b, sum G*s*branch, sum G*s) live in a per-warp SHARED-MEMORY accumulator (each lane owns
+// its columns, so plain load-add-store, no atomics): registers stay low enough for 3 CTAs / SM, which is
+// what keeps enough loads in flight to run at HBM speed.  CTA partials -> part[blockIdx][4][D].
+//   g_xout may be null (no later residual gradient), g_y may be null (LN output unused).
+constexpr int NACC = 4;
 template <int NV>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__restrict__ g_y,
                        const float *__restrict__ x_out, const float *__restrict__ mean_in,
                        const float *__restrict__ rstd_in, const float *__restrict__ ln_w,
-                       const __nv_bfloat16 *__restrict__ branch, const float *__restrict__ ls_gamma,
-                       const float *__restrict__ rowscale, int rows_per_sample, int M, float *__restrict__ g_x,
-                       __nv_bfloat16 *__restrict__ g_branch, float *__restrict__ part) {
+                       const __nv_bfloat16 *__restrict__ branch, const float *__restrict__ branch_bias,
+                       const float *__restrict__ ls_gamma, const float *__restrict__ rowscale, int rows_per_sample,
+                       int M, float *__restrict__ g_x, __nv_bfloat16 *__restrict__ g_branch,
+                       float *__restrict__ part) {
     constexpr int D = NV * 128;
-    __shared__ float red[WARPS][128];  // staging for the cross-warp column reduction (one chunk at a time)
+    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 aw[NV], ab[NV], ag[NV];  // d ln_w, d ln_b, d ls_gamma partials
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { aw[i] = ab[i] = ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    float *acc = acc_s + (size_t)warp * NACC * D;
+    for (int i = lane * 4; i < NACC * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
     for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
         const size_t base = (size_t)row * D;
         const float mean = mean_in[row], rstd = rstd_in[row];
@@ -129,8 +138,12 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
             if (g_y) {
                 float4 g = load_bf16x4(g_y + base + col);
                 float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
-                ab[i].x += g.x; ab[i].y += g.y; ab[i].z += g.z; ab[i].w += g.w;
-                aw[i].x += g.x * xh[i].x; aw[i].y += g.y * xh[i].y; aw[i].z += g.z * xh[i].z; aw[i].w += g.w * xh[i].w;
+                float4 a0 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
+                float4 a1 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
+                a0.x += g.x * xh[i].x; a0.y += g.y * xh[i].y; a0.z += g.z * xh[i].z; a0.w += g.w * xh[i].w;
+                a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
+                *reinterpret_cast<float4 *>(acc + 0 * D + col) = a0;
+                *reinterpret_cast<float4 *>(acc + 1 * D + col) = a1;
                 gy[i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
                 c1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
                 c2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
@@ -154,144 +167,215 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
             if (branch) {
                 float4 b = load_bf16x4(branch + base + col);
                 float4 gm = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-                ag[i].x += G.x * s * b.x; ag[i].y += G.y * s * b.y; ag[i].z += G.z * s * b.z; ag[i].w += G.w * s * b.w;
-                if (g_branch)
-                    store_bf16x4(g_branch + base + col, make_float4(G.x * s * gm.x, G.y * s * gm.y, G.z * s * gm.z, G.w * s * gm.w));
+                float4 a2 = *reinterpret_cast<float4 *>(acc + 2 * D + col);
+                float4 a3 = *reinterpret_cast<float4 *>(acc + 3 * D + col);
+                float4 Gs = make_float4(G.x * s, G.y * s, G.z * s, G.w * s);
+                a2.x += Gs.x * b.x; a2.y += Gs.y * b.y; a2.z += Gs.z * b.z; a2.w += Gs.w * b.w;
+                a3.x += Gs.x; a3.y += Gs.y; a3.z += Gs.z; a3.w += Gs.w;
+                *reinterpret_cast<float4 *>(acc + 2 * D + col) = a2;
+                *reinterpret_cast<float4 *>(acc + 3 * D + col) = a3;
+                if (g_branch) store_bf16x4(g_branch + base + col, make_float4(Gs.x * gm.x, Gs.y * gm.y, Gs.z * gm.z, Gs.w * gm.w));
             }
         }
     }
-    // cross-warp reduction of the column partials, one 128-column chunk at a time
-    float *outp = part + (size_t)blockIdx.x * 3 * D;
+    __syncthreads();
+    float *outp = part + (size_t)blockIdx.x * NACC * D;
+    for (int e = threadIdx.x; e < NACC * D; e += THREADS) {
+        float a = 0.f;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            float4 a = q == 0 ? aw[i] : (q == 1 ? ab[i] : ag[i]);
-            __syncthreads();
-            *reinterpret_cast<float4 *>(&red[warp][lane * 4]) = a;
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                float acc = 0.f;
-#pragma unroll
-                for (int w = 0; w < WARPS; ++w) acc += red[w][threadIdx.x];
-                outp[(size_t)q * D + i * 128 + threadIdx.x] = acc;
-            }
-        }
+        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC * D + e];
+        outp[e] = a;
     }
 }
 
-__global__ void reduce_parts_kernel(const float *__restrict__ part, int nblocks, int n, float *__restrict__ o0,
-                                    float *__restrict__ o1, float *__restrict__ o2, int D) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    float acc = 0.f;
-    for (int b = 0; b < nblocks; ++b) acc += part[(size_t)b * n + e];
-    int q = e / D, d = e - q * D;
-    float *o = q == 0 ? o0 : (q == 1 ? o1 : o2);
-    if (o) o[d] = acc;
+// sums the CTA partials and finishes the four vectors:
+//   d ln_w = P0 ; d ln_b = P1 ; d gamma_ls = P2 + bias * P3 ; d branch_bias = gamma_ls * P3
+__global__ void reduce_parts_kernel(const float *__restrict__ part, int nblocks, int D, const float *__restrict__ ls_gamma,
+                                    const float *__restrict__ branch_bias, float *__restrict__ g_ln_w,
+                                    float *__restrict__ g_ln_b, float *__restrict__ g_ls_gamma,
+                                    float *__restrict__ g_branch_bias) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float p[NACC] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < nblocks; ++b)
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) p[q] += part[((size_t)b * NACC + q) * D + d];
+    if (g_ln_w) g_ln_w[d] = p[0];
+    if (g_ln_b) g_ln_b[d] = p[1];
+    if (g_ls_gamma) g_ls_gamma[d] = p[2] + (branch_bias ? branch_bias[d] * p[3] : 0.f);
+    if (g_branch_bias) g_branch_bias[d] = (ls_gamma ? ls_gamma[d] : 1.f) * p[3];
 }
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding);
+// e = exp(-z^2) is shared with the derivative (z = x / sqrt(2) -> e = exp(-x^2 / 2)).
+__device__ __forceinline__ float erf_as(float z, float e) {
+    float az = fabsf(z);
+    float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+    float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    float r = fmaf(-poly, e, 1.f);
+    return copysignf(r, z);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float e = __expf(-0.5f * x * x);
+    return 0.5f * x * (1.f + erf_as(x * 0.70710678118654752f, e));
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    float e = __expf(-0.5f * x * x);
+    return 0.5f * (1.f + erf_as(x * 0.70710678118654752f, e)) + x * 0.3989422804014327f * e;
 }
 
-__global__ void gelu_fwd_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t n8) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
-    uint4 v = x[i];
-    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+// y = gelu(x + bias): block = one row slice of NC8 uint4 columns; rows walked with a grid stride.
+__global__ void gelu_fwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, uint4 *__restrict__ y,
+                                int M, int C8) {
+    for (int row = blockIdx.x; row < M; row += gridDim.x) {
+        for (int c = threadIdx.x; c < C8; c += blockDim.x) {
+            uint4 v = x[(size_t)row * C8 + c];
+            __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (bias) {
+                float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
+                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+            }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float2 f = __bfloat1622float2(p[k]);
-        p[k] = __floats2bfloat162_rn(gelu_f(f.x), gelu_f(f.y));
+            for (int k = 0; k < 4; ++k) {
+                float2 f = __bfloat1622float2(p[k]);
+                p[k] = __floats2bfloat162_rn(gelu_f(f.x + bb[2 * k]), gelu_f(f.y + bb[2 * k + 1]));
+            }
+            y[(size_t)row * C8 + c] = v;
+        }
     }
-    y[i] = v;
 }
 
-__global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ gy, uint4 *__restrict__ gx,
-                                size_t n8) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n8) return;
-    uint4 v = x[i], g = gy[i];
-    __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
-    __nv_bfloat162 *q = reinterpret_cast<__nv_bfloat162 *>(&g);
+// gx = gy * gelu'(x + bias); column sums of gx (= d bias) accumulate per thread, one atomicAdd per column
+// per CTA at the end (g_bias must be zeroed by the caller).
+__global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, const uint4 *__restrict__ gy,
+                                uint4 *__restrict__ gx, float *__restrict__ g_bias, int M, int C8) {
+    for (int c = threadIdx.x; c < C8; c += blockDim.x) {
+        float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (bias) {
+            float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+        }
+        for (int row = blockIdx.x; row < M; row += gridDim.x) {
+            uint4 v = x[(size_t)row * C8 + c], g = gy[(size_t)row * C8 + c];
+            __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
+            __nv_bfloat162 *q = reinterpret_cast<__nv_bfloat162 *>(&g);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float2 f = __bfloat1622float2(p[k]), h = __bfloat1622float2(q[k]);
-        p[k] = __floats2bfloat162_rn(h.x * dgelu_f(f.x), h.y * dgelu_f(f.y));
+            for (int k = 0; k < 4; ++k) {
+                float2 f = __bfloat1622float2(p[k]), h = __bfloat1622float2(q[k]);
+                float r0 = h.x * dgelu_f(f.x + bb[2 * k]), r1 = h.y * dgelu_f(f.y + bb[2 * k + 1]);
+                acc[2 * k] += r0; acc[2 * k + 1] += r1;
+                p[k] = __floats2bfloat162_rn(r0, r1);
+            }
+            gx[(size_t)row * C8 + c] = v;
+        }
+        if (g_bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(g_bias + c * 8 + k, acc[k]);
+        }
     }
-    gx[i] = v;
+}
+
+// dq, dk, dv: each [M, C] bf16 dense (what the SDPA backward returns for q/k/v views of a packed
+// [M, 3C] projection) -> dqkv [M, 3C].  One 16-byte vector per thread.
+__global__ void pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__restrict__ dk, const uint4 *__restrict__ dv,
+                                uint4 *__restrict__ out, size_t M, int C8) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t per_row = (size_t)3 * C8;
+    if (i >= M * per_row) return;
+    size_t row = i / per_row;
+    int c = (int)(i - row * per_row);
+    int which = c / C8, cc = c - which * C8;
+    const uint4 *src = which == 0 ? dq : (which == 1 ? dk : dv);
+    out[i] = src[row * C8 + cc];
 }
 
 static int bwd_grid() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 2;
+    return sms * 2;  // 2 CTAs / SM (shared-memory accumulators: 96 KB per CTA at D=768)
 }
 
 }  // namespace xqv
 
 using namespace xqv;
 
-#define XQV_DISPATCH(D, CALL)                 \
+#define XQV_DISPATCH(D, ...)                  \
     switch (D) {                               \
-        case 384: { constexpr int NV = 3; CALL; break; }   \
-        case 768: { constexpr int NV = 6; CALL; break; }   \
-        case 1024: { constexpr int NV = 8; CALL; break; }  \
+        case 384: { constexpr int NV = 3; __VA_ARGS__; break; }   \
+        case 768: { constexpr int NV = 6; __VA_ARGS__; break; }   \
+        case 1024: { constexpr int NV = 8; __VA_ARGS__; break; }  \
         default: return XQ_ERR_UNSUPPORTED;    \
     }
 
 extern "C" {
 
-size_t xq_vit_ln_bwd_workspace_bytes(int D) { return sizeof(float) * (size_t)bwd_grid() * 3 * D; }
+size_t xq_vit_ln_bwd_workspace_bytes(int D) { return sizeof(float) * (size_t)bwd_grid() * NACC * D; }
 
-int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *ls_gamma, const float *rowscale,
-                           int rows_per_sample, const float *ln_w, const float *ln_b, float eps, int M, int D,
-                           float *x_out, void *y, float *mean, float *rstd, void *stream) {
+int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *branch_bias, const float *ls_gamma,
+                           const float *rowscale, int rows_per_sample, const float *ln_w, const float *ln_b, float eps,
+                           int M, int D, float *x_out, void *y, float *mean, float *rstd, void *stream) {
     if (!x || M <= 0 || (y && (!ln_w || !ln_b)) || (!x_out && !y)) return XQ_ERR_ARG;
     if (branch && rowscale && rows_per_sample <= 0) return XQ_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = (M + WARPS - 1) / WARPS;
     XQV_DISPATCH(D, (residual_ln_fwd_kernel<NV><<<grid, THREADS, 0, st>>>(
-                        x, (const __nv_bfloat16 *)branch, ls_gamma, rowscale, rows_per_sample, ln_w, ln_b, eps, M,
-                        x_out, (__nv_bfloat16 *)y, mean, rstd)));
+                        x, (const __nv_bfloat16 *)branch, branch_bias, ls_gamma, rowscale, rows_per_sample, ln_w, ln_b,
+                        eps, M, x_out, (__nv_bfloat16 *)y, mean, rstd)));
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
 int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_out, const float *mean,
-                           const float *rstd, const float *ln_w, const void *branch, const float *ls_gamma,
-                           const float *rowscale, int rows_per_sample, int M, int D, float *g_x, void *g_branch,
-                           float *g_ln_w, float *g_ln_b, float *g_ls_gamma, void *workspace, size_t workspace_bytes,
-                           void *stream) {
+                           const float *rstd, const float *ln_w, const void *branch, const float *branch_bias,
+                           const float *ls_gamma, const float *rowscale, int rows_per_sample, int M, int D, float *g_x,
+                           void *g_branch, float *g_ln_w, float *g_ln_b, float *g_ls_gamma, float *g_branch_bias,
+                           void *workspace, size_t workspace_bytes, void *stream) {
     if (!x_out || !mean || !rstd || M <= 0 || !workspace) return XQ_ERR_ARG;
     if (g_y && !ln_w) return XQ_ERR_ARG;
     const int grid = bwd_grid();
-    if (workspace_bytes < sizeof(float) * (size_t)grid * 3 * D) return XQ_ERR_WORKSPACE;
+    if (workspace_bytes < sizeof(float) * (size_t)grid * NACC * D) return XQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float *part = (float *)workspace;
-    XQV_DISPATCH(D, (residual_ln_bwd_kernel<NV><<<grid, THREADS, 0, st>>>(
-                        g_xout, (const __nv_bfloat16 *)g_y, x_out, mean, rstd, ln_w, (const __nv_bfloat16 *)branch,
-                        ls_gamma, rowscale, rows_per_sample, M, g_x, (__nv_bfloat16 *)g_branch, part)));
+    const size_t smem = sizeof(float) * (size_t)WARPS * NACC * D;
+    XQV_DISPATCH(D, {
+        if (cudaFuncSetAttribute(residual_ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return XQ_ERR_CUDA;
+        residual_ln_bwd_kernel<NV><<<grid, THREADS, smem, st>>>(
+            g_xout, (const __nv_bfloat16 *)g_y, x_out, mean, rstd, ln_w, (const __nv_bfloat16 *)branch, branch_bias,
+            ls_gamma, rowscale, rows_per_sample, M, g_x, (__nv_bfloat16 *)g_branch, part);
+    });
     if (cudaGetLastError() != cudaSuccess) return XQ_ERR_CUDA;
-    int n = 3 * D;
-    reduce_parts_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, grid, n, g_ln_w, g_ln_b, g_ls_gamma, D);
+    reduce_parts_kernel<<<(D + 127) / 128, 128, 0, st>>>(part, grid, D, ls_gamma, branch_bias, g_ln_w, g_ln_b,
+                                                        branch ? g_ls_gamma : nullptr, branch ? g_branch_bias : nullptr);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
-int xq_vit_gelu_fwd(const void *x, void *y, size_t n, void *stream) {
-    if (!x || !y || (n & 7)) return XQ_ERR_ARG;
-    size_t n8 = n / 8;
-    gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x, (uint4 *)y, n8);
+int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, size_t M, int C, void *stream) {
+    if (!dq || !dk || !dv || !dqkv || M == 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
+    size_t n = M * 3 * (size_t)(C / 8);
+    pack_qkv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv, (uint4 *)dqkv, M, C / 8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
-int xq_vit_gelu_bwd(const void *x, const void *gy, void *gx, size_t n, void *stream) {
-    if (!x || !gy || !gx || (n & 7)) return XQ_ERR_ARG;
-    size_t n8 = n / 8;
-    gelu_bwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x, (const uint4 *)gy,
-                                                                                  (uint4 *)gx, n8);
+int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, void *stream) {
+    if (!x || !y || M <= 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
+    int C8 = C / 8;
+    int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
+    int grid = M < 148 * 8 ? M : 148 * 8;
+    gelu_fwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)x, bias, (uint4 *)y, M, C8);
+    return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
+}
+
+int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *g_bias, int M, int C, void *stream) {
+    if (!x || !gy || !gx || M <= 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int C8 = C / 8;
+    int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
+    int grid = M < 148 * 8 ? M : 148 * 8;
+    if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
+    gelu_bwd_kernel<<<grid, threads, 0, st>>>((const uint4 *)x, bias, (const uint4 *)gy, (uint4 *)gx, g_bias, M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 

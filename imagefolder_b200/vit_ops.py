@@ -14,15 +14,17 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _capi as C
+from ._capi import call as _call, lib as _lib, ptr as _ptr, stream_ptr as _stream
 
 _SUPPORTED_D = (384, 768, 1024)
 
 
 class _ResidualLN(torch.autograd.Function):
-    """(x, branch, ls_gamma, rowscale, ln_w, ln_b) -> (x_out fp32, y bf16)."""
+    """(x, branch, branch_bias, ls_gamma, rowscale, ln_w, ln_b) -> (x_out fp32, y bf16)
+    x_out = x + rowscale * ls_gamma * (branch + branch_bias);  y = LayerNorm(x_out)."""
 
     @staticmethod
-    def forward(ctx, x, branch, ls_gamma, rowscale, ln_w, ln_b, eps: float):
+    def forward(ctx, x, branch, branch_bias, ls_gamma, rowscale, ln_w, ln_b, eps: float):
         Bn, S, D = x.shape
         M = Bn * S
         x = x.contiguous()
@@ -37,17 +39,17 @@ class _ResidualLN(torch.autograd.Function):
         mean = torch.empty(M, dtype=torch.float32, device=x.device)
         rstd = torch.empty(M, dtype=torch.float32, device=x.device)
         L = C.lib()
-        C.call("xq_vit_residual_ln_fwd", 1, L.xq_vit_residual_ln_fwd, C.ptr(x), C.ptr(branch), C.ptr(ls_gamma),
-               C.ptr(rowscale), S, C.ptr(ln_w), C.ptr(ln_b), float(eps), M, D, C.ptr(x_out), C.ptr(y), C.ptr(mean),
-               C.ptr(rstd), C.stream_ptr(x.device))
-        ctx.save_for_backward(x_out, mean, rstd, ln_w, branch, ls_gamma, rowscale)
+        C.call("xq_vit_residual_ln_fwd", 1, L.xq_vit_residual_ln_fwd, C.ptr(x), C.ptr(branch), C.ptr(branch_bias),
+               C.ptr(ls_gamma), C.ptr(rowscale), S, C.ptr(ln_w), C.ptr(ln_b), float(eps), M, D, C.ptr(x_out), C.ptr(y),
+               C.ptr(mean), C.ptr(rstd), C.stream_ptr(x.device))
+        ctx.save_for_backward(x_out, mean, rstd, ln_w, branch, branch_bias, ls_gamma, rowscale)
         ctx.shape = (Bn, S, D)
         ctx.set_materialize_grads(False)
         return x_out, y
 
     @staticmethod
     def backward(ctx, g_xout, g_y):
-        x_out, mean, rstd, ln_w, branch, ls_gamma, rowscale = ctx.saved_tensors
+        x_out, mean, rstd, ln_w, branch, branch_bias, ls_gamma, rowscale = ctx.saved_tensors
         Bn, S, D = ctx.shape
         M = Bn * S
         dev = x_out.device
@@ -64,43 +66,107 @@ class _ResidualLN(torch.autograd.Function):
         g_w = torch.empty_like(ln_w)
         g_b = torch.empty_like(ln_w)
         g_g = torch.empty_like(ls_gamma) if (branch is not None and ls_gamma is not None) else None
+        g_bb = torch.empty_like(branch_bias) if (branch is not None and branch_bias is not None) else None
         L = C.lib()
         ws = C.workspace(L.xq_vit_ln_bwd_workspace_bytes(D), dev)
         C.call("xq_vit_residual_ln_bwd", 2, L.xq_vit_residual_ln_bwd, C.ptr(g_xout), C.ptr(g_y), C.ptr(x_out),
-               C.ptr(mean), C.ptr(rstd), C.ptr(ln_w), C.ptr(branch), C.ptr(ls_gamma), C.ptr(rowscale), S, M, D,
-               C.ptr(g_x), C.ptr(g_branch), C.ptr(g_w), C.ptr(g_b), C.ptr(g_g), C.ptr(ws), ws.numel(),
-               C.stream_ptr(dev))
-        return g_x, g_branch, g_g, None, g_w, g_b, None
+               C.ptr(mean), C.ptr(rstd), C.ptr(ln_w), C.ptr(branch), C.ptr(branch_bias), C.ptr(ls_gamma),
+               C.ptr(rowscale), S, M, D, C.ptr(g_x), C.ptr(g_branch), C.ptr(g_w), C.ptr(g_b), C.ptr(g_g), C.ptr(g_bb),
+               C.ptr(ws), ws.numel(), C.stream_ptr(dev))
+        return g_x, g_branch, g_bb, g_g, None, g_w, g_b, None
 
 
-def residual_ln(x, branch, ls_gamma, rowscale, ln_w, ln_b, eps=1e-6):
-    return _ResidualLN.apply(x, branch, ls_gamma, rowscale, ln_w, ln_b, eps)
+def residual_ln(x, branch, branch_bias, ls_gamma, rowscale, ln_w, ln_b, eps=1e-6):
+    return _ResidualLN.apply(x, branch, branch_bias, ls_gamma, rowscale, ln_w, ln_b, eps)
 
 
-class _Gelu(torch.autograd.Function):
+class _GeluBias(torch.autograd.Function):
+    """y = GELU(x + bias), x bf16 [..., C] (the fc1 GEMM output WITHOUT its bias), bias fp32 [C]."""
+
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, bias):
         x = x.contiguous()
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
         y = torch.empty_like(x)
         L = C.lib()
-        C.call("xq_vit_gelu_fwd", 1, L.xq_vit_gelu_fwd, C.ptr(x), C.ptr(y), x.numel(), C.stream_ptr(x.device))
-        ctx.save_for_backward(x)
+        C.call("xq_vit_gelu_fwd", 1, L.xq_vit_gelu_fwd, C.ptr(x), C.ptr(bias), C.ptr(y), M, Cc, C.stream_ptr(x.device))
+        ctx.save_for_backward(x, bias)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        (x,) = ctx.saved_tensors
+        x, bias = ctx.saved_tensors
         gy = gy.contiguous()
         if gy.dtype != torch.bfloat16:
             gy = gy.to(torch.bfloat16)
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
         gx = torch.empty_like(x)
+        gb = torch.empty_like(bias) if bias is not None else None
         L = C.lib()
-        C.call("xq_vit_gelu_bwd", 1, L.xq_vit_gelu_bwd, C.ptr(x), C.ptr(gy), C.ptr(gx), x.numel(), C.stream_ptr(x.device))
-        return gx
+        C.call("xq_vit_gelu_bwd", 1, L.xq_vit_gelu_bwd, C.ptr(x), C.ptr(bias), C.ptr(gy), C.ptr(gx), C.ptr(gb), M, Cc,
+               C.stream_ptr(x.device))
+        return gx, gb
 
 
-def gelu_bf16(x):
-    return _Gelu.apply(x)
+def gelu_bias(x, bias=None):
+    return _GeluBias.apply(x, bias)
+
+
+class _PackedAttention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d)) v on the packed projection qkv [B,N,3*H*hd] (vision_transformer.py:175-191).
+
+    The attention itself is the SDPA library kernel; this wrapper only removes the layout glue autograd
+    adds around it: q/k/v are strided views of the packed tensor (no copies in forward; the library
+    allocates the output in [B,N,H,hd] order so the head merge is a view) and the three gradients are
+    re-packed into d(qkv) by ONE vector kernel instead of stack + permute + contiguous."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads: int, dropout_p: float):
+        B, N, C3 = qkv.shape
+        C = C3 // 3
+        hd = C // num_heads
+        with torch.enable_grad():
+            src = qkv.detach().view(B, N, 3, num_heads, hd)
+            q = src[:, :, 0].transpose(1, 2).requires_grad_(True)
+            k = src[:, :, 1].transpose(1, 2).requires_grad_(True)
+            v = src[:, :, 2].transpose(1, 2).requires_grad_(True)
+            out = F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p)
+        ctx.inner = (q, k, v, out)
+        ctx.dims = (B, N, C)
+        return out.detach().transpose(1, 2).reshape(B, N, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, out = ctx.inner
+        ctx.inner = None
+        B, N, C = ctx.dims
+        H, hd = q.shape[1], q.shape[3]
+        g = g.reshape(B, N, H, hd).transpose(1, 2)
+        dq, dk, dv = torch.autograd.grad(out, (q, k, v), g)
+        dqkv = torch.empty(B, N, 3 * C, dtype=dq.dtype, device=dq.device)
+        flat = [t.transpose(1, 2) for t in (dq, dk, dv)]            # [B,N,H,hd]
+        if all(t.is_contiguous() for t in flat) and dq.dtype == torch.bfloat16:
+            L = _lib()
+            _call("xq_vit_pack_qkv", 1, L.xq_vit_pack_qkv, _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(dqkv),
+                  B * N, C, _stream(dq.device))
+        else:  # layout the library did not produce in our runs; keep correctness
+            torch.stack([t.reshape(B, N, C) for t in flat], dim=2, out=dqkv.view(B, N, 3, C))
+        return dqkv, None, None
+
+
+def packed_attention(qkv, num_heads, dropout_p=0.0):
+    return _PackedAttention.apply(qkv, num_heads, dropout_p)
+
+
+def attention_forward(attn, y):
+    """Attention.forward (vision_transformer.py:173-197) on the fused path (no qk_norm, no mask)."""
+    if not isinstance(attn.q_norm, nn.Identity) or not isinstance(attn.k_norm, nn.Identity):
+        return attn(y)
+    qkv = attn.qkv(y)
+    o = packed_attention(qkv, attn.num_heads, attn.attn_drop.p if attn.training else 0.0)
+    return F.linear(o, attn.proj.weight)      # the proj bias is folded into the next residual_ln
 
 
 def _droppath_scale(mod, batch: int, device):
@@ -135,16 +201,18 @@ def run_blocks(vit, x, attn_mask=None):
     Bn = x.shape[0]
     dev = x.device
     x = x.float()
-    branch = gamma = rs = None
+    branch = bias = gamma = rs = None
     for blk in vit.blocks:
-        x, y = residual_ln(x, branch, gamma, rs, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-        a = blk.attn(y)
+        x, y = residual_ln(x, branch, bias, gamma, rs, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+        plain_attn = isinstance(blk.attn.q_norm, nn.Identity) and isinstance(blk.attn.k_norm, nn.Identity)
+        a = attention_forward(blk.attn, y)
         g1 = blk.ls1.gamma if hasattr(blk.ls1, "gamma") else None
-        x, y = residual_ln(x, a, g1, _droppath_scale(blk.drop_path1, Bn, dev), blk.norm2.weight, blk.norm2.bias,
-                           blk.norm2.eps)
-        h = gelu_bf16(blk.mlp.fc1(y))
-        branch = blk.mlp.fc2(h)
+        x, y = residual_ln(x, a, blk.attn.proj.bias if plain_attn else None, g1,
+                           _droppath_scale(blk.drop_path1, Bn, dev), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+        h = gelu_bias(F.linear(y, blk.mlp.fc1.weight), blk.mlp.fc1.bias)     # fc1 bias folded into the GELU kernel
+        branch = F.linear(h, blk.mlp.fc2.weight)                             # fc2 bias folded into the next residual_ln
+        bias = blk.mlp.fc2.bias
         gamma = blk.ls2.gamma if hasattr(blk.ls2, "gamma") else None
         rs = _droppath_scale(blk.drop_path2, Bn, dev)
-    _, y = residual_ln(x, branch, gamma, rs, vit.norm.weight, vit.norm.bias, vit.norm.eps)
+    _, y = residual_ln(x, branch, bias, gamma, rs, vit.norm.weight, vit.norm.bias, vit.norm.eps)
     return y

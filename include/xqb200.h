@@ -178,23 +178,30 @@ int xq_usage_ema(float *ema, const float *hit, int rows, int V, int record_hit, 
  * Residual stream fp32 [M,D], GEMM operands bf16 (what bf16 autocast gives the reference).
  * D in {384, 768, 1024}.  `branch`, `y`, `g_y`, `g_branch` are bf16 [M,D].
  * ------------------------------------------------------------------------------------------ */
-/*   x_out = x + rowscale[row / rows_per_sample] * ls_gamma[d] * branch   (branch may be NULL: x_out = x)
+/*   x_out = x + rowscale[row / rows_per_sample] * ls_gamma[d] * (branch + branch_bias[d])
+ *           (branch may be NULL: x_out = x; branch_bias = bias of the GEMM that produced `branch`, folded here
+ *            so that its gradient is a free column sum of the backward kernel; may be NULL)
  *   y     = LayerNorm(x_out; eps) * ln_w + ln_b   (bf16; may be NULL)   mean / rstd [M] saved for backward
  *   rowscale [B] = DropPath keep mask / keep_prob (NULL = 1);  x_out may alias x or be NULL */
-int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *ls_gamma, const float *rowscale,
-                           int rows_per_sample, const float *ln_w, const float *ln_b, float eps, int M, int D,
-                           float *x_out, void *y, float *mean, float *rstd, void *stream);
+int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *branch_bias, const float *ls_gamma,
+                           const float *rowscale, int rows_per_sample, const float *ln_w, const float *ln_b, float eps,
+                           int M, int D, float *x_out, void *y, float *mean, float *rstd, void *stream);
 size_t xq_vit_ln_bwd_workspace_bytes(int D);
 /*   G = g_xout + LayerNorm^T(g_y)  -> g_x [M,D] fp32 ; g_branch = G * rowscale * ls_gamma (bf16)
- *   g_ln_w, g_ln_b, g_ls_gamma [D] overwritten (any may be NULL) */
+ *   g_ln_w, g_ln_b, g_ls_gamma, g_branch_bias [D] overwritten (any may be NULL) */
 int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_out, const float *mean,
-                           const float *rstd, const float *ln_w, const void *branch, const float *ls_gamma,
-                           const float *rowscale, int rows_per_sample, int M, int D, float *g_x, void *g_branch,
-                           float *g_ln_w, float *g_ln_b, float *g_ls_gamma, void *workspace,
-                           size_t workspace_bytes, void *stream);
-/*   exact (erf) GELU on bf16, n % 8 == 0 (timm Mlp act_layer=nn.GELU) */
-int xq_vit_gelu_fwd(const void *x, void *y, size_t n, void *stream);
-int xq_vit_gelu_bwd(const void *x, const void *gy, void *gx, size_t n, void *stream);
+                           const float *rstd, const float *ln_w, const void *branch, const float *branch_bias,
+                           const float *ls_gamma, const float *rowscale, int rows_per_sample, int M, int D, float *g_x,
+                           void *g_branch, float *g_ln_w, float *g_ln_b, float *g_ls_gamma, float *g_branch_bias,
+                           void *workspace, size_t workspace_bytes, void *stream);
+/*   gradient re-packing of the fused qkv projection (vision_transformer.py:175-176): dq, dk, dv [M,C] bf16
+ *   dense -> dqkv [M,3C]; replaces autograd's stack + permute + contiguous copies */
+int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, size_t M, int C, void *stream);
+/*   y = GELU(x + bias) exact-erf form (timm Mlp act_layer=nn.GELU), x / y bf16 [M,C], bias fp32 [C] or NULL,
+ *   C % 8 == 0.  Backward also returns g_bias [C] = column sums of gx (may be NULL). */
+int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, void *stream);
+int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *g_bias, int M, int C,
+                    void *stream);
 
 #ifdef __cplusplus
 }

@@ -8,12 +8,13 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def ref_residual_ln(x, branch, gamma, rs, w, b, eps, S):
+def ref_residual_ln(x, branch, gamma, rs, w, b, eps, S, bbias=None):
     x = x.double()
     if branch is not None:
         s = rs.double().repeat_interleave(S).view(x.shape[0], x.shape[1], 1) if rs is not None else 1.0
         g = gamma.double() if gamma is not None else 1.0
-        x = x + s * g * branch.double()
+        br = branch.double() + (bbias.double() if bbias is not None else 0.0)
+        x = x + s * g * br
     y = F.layer_norm(x, (x.shape[-1],), w.double(), b.double(), eps)
     return x, y
 
@@ -30,9 +31,11 @@ def test_residual_ln_fwd_bwd(D, Bn, S, with_branch):
     rs = torch.tensor([0.0, 1 / 0.9, 1 / 0.9][:Bn], device=dev) if with_branch else None
     w = (torch.rand(D, device=dev) + 0.5).requires_grad_(True)
     b = torch.randn(D, device=dev, requires_grad=True)
-    x_out, y = residual_ln(x, branch, gamma, rs, w, b, 1e-6)
+    bbias = torch.randn(D, device=dev, requires_grad=True) if with_branch else None
+    x_out, y = residual_ln(x, branch, bbias, gamma, rs, w, b, 1e-6)
     assert x_out.dtype == torch.float32 and y.dtype == torch.bfloat16
-    xr, yr = ref_residual_ln(x.detach(), branch.detach() if with_branch else None, gamma, rs, w, b, 1e-6, S)
+    with torch.no_grad():
+        xr, yr = ref_residual_ln(x.detach(), branch.detach() if with_branch else None, gamma, rs, w, b, 1e-6, S, bbias)
     np.testing.assert_allclose(x_out.detach().cpu().numpy(), xr.float().cpu().numpy(), rtol=1e-6, atol=1e-6)
     # y is rounded to bf16: 2^-8 relative
     np.testing.assert_allclose(y.float().detach().cpu().numpy(), yr.detach().float().cpu().numpy(), rtol=8e-3, atol=8e-3)
@@ -44,7 +47,8 @@ def test_residual_ln_fwd_bwd(D, Bn, S, with_branch):
     br2 = branch.detach().double().requires_grad_(True) if with_branch else None
     ga2 = gamma.detach().double().requires_grad_(True) if with_branch else None
     w2, b2 = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
-    xo2, y2 = ref_residual_ln(x2, br2, ga2, rs, w2, b2, 1e-6, S)
+    bb2 = bbias.detach().double().requires_grad_(True) if with_branch else None
+    xo2, y2 = ref_residual_ln(x2, br2, ga2, rs, w2, b2, 1e-6, S, bb2)
     (xo2 * g_xo.double()).sum().add((y2 * g_y.double()).sum()).backward()
 
     def chk(a, r, rtol):
@@ -56,6 +60,7 @@ def test_residual_ln_fwd_bwd(D, Bn, S, with_branch):
     if with_branch:
         chk(branch.grad, br2.grad, 8e-3)       # bf16 output
         chk(gamma.grad, ga2.grad, 1e-4)
+        chk(bbias.grad, bb2.grad, 1e-4)
 
 
 def test_residual_ln_none_grads():
@@ -64,24 +69,32 @@ def test_residual_ln_none_grads():
     x = torch.randn(2, 5, 768, device="cuda", requires_grad=True)
     w = torch.ones(768, device="cuda", requires_grad=True)
     b = torch.zeros(768, device="cuda", requires_grad=True)
-    _, y = residual_ln(x, None, None, None, w, b, 1e-6)
-    y.float().pow(2).sum().backward()
+    _, y = residual_ln(x, None, None, None, None, w, b, 1e-6)
+    g = torch.randn_like(y)
+    y.backward(g)
     x2 = x.detach().double().requires_grad_(True)
-    F.layer_norm(x2, (768,), w.detach().double(), b.detach().double(), 1e-6).pow(2).sum().backward()
-    np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.float().cpu().numpy(), rtol=2e-2, atol=2e-2 * float(x2.grad.abs().max()))
+    F.layer_norm(x2, (768,), w.detach().double(), b.detach().double(), 1e-6).backward(g.double())
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x2.grad.float().cpu().numpy(), rtol=1e-4, atol=1e-4 * float(x2.grad.abs().max()))
 
 
 def test_gelu_bf16():
-    from imagefolder_b200.vit_ops import gelu_bf16
-    x = (torch.randn(4, 33, 3072, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
-    y = gelu_bf16(x)
-    ref = F.gelu(x.detach().float())
-    np.testing.assert_allclose(y.float().detach().cpu().numpy(), ref.cpu().numpy(), rtol=8e-3, atol=1e-3)
-    g = torch.randn_like(y)
-    y.backward(g)
-    x2 = x.detach().float().requires_grad_(True)
-    F.gelu(x2).backward(g.float())
-    np.testing.assert_allclose(x.grad.float().cpu().numpy(), x2.grad.cpu().numpy(), rtol=8e-3, atol=4e-3)
+    from imagefolder_b200.vit_ops import gelu_bias
+    for C in (3072, 1536, 64):
+        x = (torch.randn(4, 33, C, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
+        bias = torch.randn(C, device="cuda", requires_grad=True)
+        y = gelu_bias(x, bias)
+        x2 = x.detach().double().requires_grad_(True)
+        b2 = bias.detach().double().requires_grad_(True)
+        ref = F.gelu(x2 + b2)
+        np.testing.assert_allclose(y.float().detach().cpu().numpy(), ref.detach().float().cpu().numpy(), rtol=8e-3, atol=2e-3)
+        g = torch.randn_like(y)
+        y.backward(g)
+        ref.backward(g.double())
+        np.testing.assert_allclose(x.grad.float().cpu().numpy(), x2.grad.float().cpu().numpy(), rtol=8e-3, atol=8e-3)
+        # bias grad = column sums of bf16-rounded gx
+        np.testing.assert_allclose(bias.grad.cpu().numpy(), b2.grad.float().cpu().numpy(), rtol=2e-2, atol=0.15)
+    y = gelu_bias((torch.randn(2, 8, device="cuda")).to(torch.bfloat16), None)
+    assert y.shape == (2, 8)
 
 
 def test_fused_blocks_match_module_path():
@@ -105,7 +118,27 @@ def test_fused_blocks_match_module_path():
         finally:
             vit_ops.fused_path_ok = orig
     assert y_fused.dtype == torch.bfloat16
-    a, b = y_fused.float().cpu().numpy(), y_plain.float().cpu().numpy()
+    a, b = y_fused.detach().float().cpu().numpy(), y_plain.detach().float().cpu().numpy()
     # both are bf16-GEMM pipelines; they differ only by rounding order
     assert np.abs(a - b).max() < 0.06 * np.abs(b).max()
     assert np.corrcoef(a.ravel(), b.ravel())[0, 1] > 0.9995
+
+
+def test_packed_attention_matches_explicit_softmax():
+    from imagefolder_b200.vit_ops import packed_attention
+    torch.manual_seed(3)
+    B, N, H, hd = 3, 77, 6, 64
+    C = H * hd
+    qkv = torch.randn(B, N, 3 * C, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    o = packed_attention(qkv, H)
+    assert o.shape == (B, N, C)
+    g = torch.randn_like(o)
+    o.backward(g)
+    q2 = qkv.detach().double().requires_grad_(True)
+    t = q2.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    att = ((t[0] * hd ** -0.5) @ t[1].transpose(-2, -1)).softmax(-1)
+    ref = (att @ t[2]).transpose(1, 2).reshape(B, N, C)
+    ref.backward(g.double())
+    np.testing.assert_allclose(o.float().detach().cpu().numpy(), ref.detach().float().cpu().numpy(), rtol=2e-2, atol=2e-2)
+    gr = q2.grad.float().cpu().numpy()
+    np.testing.assert_allclose(qkv.grad.float().cpu().numpy(), gr, rtol=3e-2, atol=3e-2 * float(np.abs(gr).max()))
