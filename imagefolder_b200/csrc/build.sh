@@ -7,8 +7,9 @@ mkdir -p "$OUT"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false --compiler-options -fPIC"
 nvcc $FLAGS -c "$HERE/vq_kernels.cu" -o "$OUT/vq_kernels.o" "$@" &
 nvcc $FLAGS -c "$HERE/ms_kernels.cu" -o "$OUT/ms_kernels.o" "$@" &
+nvcc $FLAGS -c "$HERE/vq_tc_kernel.cu" -o "$OUT/vq_tc_kernel.o" "$@" &
 # ViT glue kernels carry no index decisions: default contraction (-fmad=true)
 nvcc ${FLAGS/-fmad=false/} -c "$HERE/vit_kernels.cu" -o "$OUT/vit_kernels.o" "$@" &
 wait
-nvcc -shared -o "$OUT/libxqb200.so" "$OUT/vq_kernels.o" "$OUT/ms_kernels.o" "$OUT/vit_kernels.o" -lcudart
+nvcc -shared -o "$OUT/libxqb200.so" "$OUT/vq_kernels.o" "$OUT/vq_tc_kernel.o" "$OUT/ms_kernels.o" "$OUT/vit_kernels.o" -lcudart
 echo "$OUT/libxqb200.so"

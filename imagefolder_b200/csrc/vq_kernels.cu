@@ -14,6 +14,8 @@
 //   rank_select_kernel     j-th nearest code per row (perturbation), radix select in smem
 //   perturb_backward_kernel
 //   usage_ema_kernel
+#include <cstdlib>
+
 #include "xq_common.cuh"
 
 namespace xq {
@@ -465,6 +467,21 @@ __global__ void usage_ema_kernel(float *__restrict__ ema, const float *__restric
 
 static int vpad(int V) { return (V + TILE_V - 1) / TILE_V * TILE_V; }
 
+// vq_tc_kernel.cu
+size_t vq_tc_workspace_bytes(int B, int C, int HW, int V);
+bool vq_tc_supported(int C, int V, int codebook_norm);
+int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, int ste_value, float beta, int64_t *idx,
+                  float *out, float *loss, float *hist, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// XQ_VQ_ALGO=exact|tc|auto (default auto): which search kernel xq_vq_forward uses.  Both give the same bits.
+static int vq_algo() {
+    const char *e = getenv("XQ_VQ_ALGO");
+    if (!e) return 0;
+    if (e[0] == 'e') return 1;
+    if (e[0] == 't') return 2;
+    return 0;
+}
+
 }  // namespace xq
 
 using namespace xq;
@@ -488,8 +505,10 @@ size_t xq_vq_workspace_bytes(int B, int C, int HW, int V) {
     if (B <= 0 || C <= 0 || HW <= 0 || V <= 0) return 0;
     size_t Vp = (size_t)vpad(V);
     size_t ctas = ((size_t)B * HW + TILE_R - 1) / TILE_R;
-    return align_up(sizeof(float) * Vp * C, 256) + align_up(sizeof(float) * Vp, 256) +
-           align_up(sizeof(float) * ctas, 256);
+    size_t exact = align_up(sizeof(float) * Vp * C, 256) + align_up(sizeof(float) * Vp, 256) +
+                   align_up(sizeof(float) * ctas, 256);
+    size_t tc = vq_tc_workspace_bytes(B, C, HW, V);
+    return exact > tc ? exact : tc;
 }
 
 int xq_vq_forward(const float *z, const float *E, int B, int C, int HW, int V, int codebook_norm, int ste_value,
@@ -498,9 +517,18 @@ int xq_vq_forward(const float *z, const float *E, int B, int C, int HW, int V, i
     if (!z || !E || !idx || !out || !workspace) return XQ_ERR_ARG;
     if (B <= 0 || C <= 0 || HW <= 0 || V <= 0) return XQ_ERR_ARG;
     if (workspace_bytes < xq_vq_workspace_bytes(B, C, HW, V)) return XQ_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int algo = vq_algo();
+    if (algo != 1 && vq_tc_supported(C, V, codebook_norm)) {
+        // tcgen05 screening + exact rescoring (bit-identical to the CUDA-core kernel below)
+        int rc = vq_tc_forward(z, E, B, C, HW, V, ste_value, beta, idx, out, loss, hist, workspace, workspace_bytes, stream);
+        if (rc != XQ_ERR_UNSUPPORTED) return rc;
+        if (algo == 2) return rc;
+    } else if (algo == 2) {
+        return XQ_ERR_UNSUPPORTED;
+    }
     size_t smem = search_smem_bytes(C);
     if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
-    cudaStream_t stream = (cudaStream_t)stream_;
     const int Vp = vpad(V);
     const int N = B * HW;
     char *ws = (char *)workspace;

@@ -1,0 +1,447 @@
+// vq_tc_kernel.cu -- tcgen05 / TMEM / TMA version of the fused VQ search (sm_100a).
+//
+// Same contract and same BIT-EXACT results as vq_search_kernel (vq_kernels.cu), reached differently:
+//
+//   screening   the -2<z,c> inner products of a 128-row x 256-code tile are computed by ONE thread issuing
+//               tcgen05.mma.kind::tf32 (operands in 128B-swizzled shared memory: rows written by the CTA,
+//               code tiles streamed by TMA), accumulators in TMEM (2 x 256 columns, double buffered);
+//   epilogue    4 warps read their TMEM lanes with tcgen05.ld and keep, per row, the few codes whose
+//               approximate score is within W of the running maximum;
+//   rescoring   only those candidates (1.1 per row on average) are re-scored with the canonical fp32
+//               arithmetic (fmaf chain, d = (zz+ee) - 2 dot, first index on ties) -> the index equals the
+//               exact kernel's and the oracle's, because the true argmin is provably among the candidates.
+//
+// Error bound (codebook_norm=1, |z| = |c| = 1 up to 1e-6): TF32 operands carry <= 2^-10 relative error
+// each, so |dot_tf32 - dot| <= 2^-9 * sum|z_k c_k| <= 1.96e-3.  We use eps = 2.5e-3 and keep every code with
+// score >= running_max - (2 eps + 2e-6)  (the 2e-6 covers the fp32 rounding of zz + ee in the canonical key).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (TMEM lane quadrant = warp_id % 4).  Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA),
+// tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
+#include <cuda.h>
+
+#include "xq_common.cuh"
+
+namespace xq {
+
+constexpr int TC_BM = 128;       // rows per CTA  (UMMA M)
+constexpr int TC_BN = 256;       // codes per tile (UMMA N)
+constexpr int TC_THREADS = 192;
+constexpr int TC_CAP = 16;       // candidate slots per row
+constexpr float TC_EPS = 2.5e-3f;
+constexpr float TC_W = 2.0f * TC_EPS + 2e-6f;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row atoms 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address >> 4            bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B   bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                         // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 256
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B operand made of 32-float (128 B) K chunks
+__device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows_per_chunk) {
+    int kc = k >> 5, kk = k & 31;
+    return (uint32_t)(kc * rows_per_chunk * 128 + row * 128 + (((kk >> 2) ^ (row & 7)) << 4) + ((kk & 3) << 2));
+}
+
+// slow path of the epilogue (a handful of calls per row): remember a candidate, compacting the list when full
+__device__ __noinline__ void cand_push(float score, int code, float *cs, int *cv, int &cnt, int &overflow,
+                                       float &runmax, float &thr) {
+    if (cnt == TC_CAP) {  // drop entries that fell below the threshold since they were stored
+        int w = 0;
+        for (int e = 0; e < TC_CAP; ++e)
+            if (cs[e] >= thr) { cs[w] = cs[e]; cv[w] = cv[e]; ++w; }
+        cnt = w;
+    }
+    if (cnt < TC_CAP) { cs[cnt] = score; cv[cnt] = code; ++cnt; }
+    else overflow = 1;
+    if (score > runmax) { runmax = score; thr = runmax - TC_W; }
+}
+
+struct TcSmem {
+    float *A;        // [C/32][128][32]  swizzled
+    float *B;        // [NSTAGE][C/32][256][32] swizzled (TMA)
+    float *cand_s;   // [128][CAP]
+    int *cand_v;     // [128][CAP]
+    float *zz, *red;
+    int *idx;
+    uint64_t *full, *empty, *tfull, *tempty;
+    uint32_t *tmem_ptr;
+};
+
+static size_t tc_smem_bytes(int C, int nstage) {
+    size_t b = 1024;                                        // alignment slack
+    b += (size_t)TC_BM * C * 4;                             // A
+    b += (size_t)nstage * TC_BN * C * 4;                    // B
+    b += (size_t)TC_BM * TC_CAP * 8;                        // candidates
+    b += (size_t)TC_BM * 4 * 2 + 32 * 4;                    // zz, idx, red
+    b += 8 * (2 * 8 + 4) + 16;                              // barriers + tmem ptr
+    return b;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__restrict__ z, const float *__restrict__ E,
+                    const float *__restrict__ En, const float *__restrict__ ee, int N, int C, int HW, int V, int Vpad,
+                    int nstage, int ste_value, int64_t *__restrict__ idx_out, float *__restrict__ out,
+                    float *__restrict__ partial, float *__restrict__ hist) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    TcSmem s;
+    s.A = (float *)base;
+    s.B = (float *)(base + (size_t)TC_BM * C * 4);
+    uint8_t *p = base + (size_t)TC_BM * C * 4 + (size_t)nstage * TC_BN * C * 4;
+    s.cand_s = (float *)p; p += (size_t)TC_BM * TC_CAP * 4;
+    s.cand_v = (int *)p; p += (size_t)TC_BM * TC_CAP * 4;
+    s.zz = (float *)p; p += TC_BM * 4;
+    s.idx = (int *)p; p += TC_BM * 4;
+    s.red = (float *)p; p += 32 * 4;
+    s.full = (uint64_t *)p; p += 8 * 8;
+    s.empty = (uint64_t *)p; p += 8 * 8;
+    s.tfull = (uint64_t *)p; p += 2 * 8;
+    s.tempty = (uint64_t *)p; p += 2 * 8;
+    s.tmem_ptr = (uint32_t *)p;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * TC_BM;
+    const int KC = C >> 5;                       // 128-byte K chunks
+    const int T = Vpad / TC_BN;
+    const uint32_t stage_bytes = (uint32_t)TC_BN * C * 4;
+
+    if (tid == 0) {
+        for (int i = 0; i < nstage; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.tfull[i], 1); mbar_init(&s.tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_ptr)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // rows: normalise (canonical chain) and store into the swizzled A operand; threads 0..127 own one row each
+    if (tid < TC_BM) {
+        const int n = row0 + tid;
+        float den = 1.f, zz = 0.f;
+        if (n < N) {
+            const int b = n / HW, pp = n - b * HW;
+            const float *zp = z + (size_t)b * C * HW + pp;
+            float ss = 0.f;
+            for (int k = 0; k < C; ++k) { float x = zp[(size_t)k * HW]; ss = fmaf(x, x, ss); }
+            den = fmaxf(sqrtf(ss), XQ_EPS);
+            for (int k = 0; k < C; ++k) {
+                float x = zp[(size_t)k * HW] / den;
+                zz = fmaf(x, x, zz);
+                *(float *)((uint8_t *)s.A + sw128_off(tid, k, TC_BM)) = x;
+            }
+        } else {
+            for (int k = 0; k < C; ++k) *(float *)((uint8_t *)s.A + sw128_off(tid, k, TC_BM)) = 0.f;
+        }
+        s.zz[tid] = zz;
+    }
+    fence_async_smem();            // generic-proxy stores to A -> visible to the async proxy (tcgen05.mma)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s.tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int t = 0; t < T; ++t) {
+                const int st = t % nstage;
+                mbar_wait(&s.empty[st], ((t / nstage) & 1) ^ 1);
+                mbar_expect_tx(&s.full[st], stage_bytes);
+                float *dst = s.B + (size_t)st * TC_BN * C;
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_load_2d(dst + (size_t)kc * TC_BN * 32, &tmB, kc * 32, t * TC_BN, &s.full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+            const uint32_t a_addr = smem_u32(s.A);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % nstage, as = t & 1;
+                mbar_wait(&s.tempty[as], ((t >> 1) & 1) ^ 1);
+                mbar_wait(&s.full[st], (t / nstage) & 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(s.B + (size_t)st * TC_BN * C);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
+                for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        uint64_t ad = umma_desc_sw128(a_addr + kc * TC_BM * 128 + k4 * 32);
+                        uint64_t bd = umma_desc_sw128(b_addr + kc * TC_BN * 128 + k4 * 32);
+                        umma_tf32(d_tmem, ad, bd, idesc, (kc | k4) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&s.empty[st]);    // smem stage free once these MMAs retire
+                umma_commit(&s.tfull[as]);    // accumulator ready
+            }
+        }
+    } else {
+        // ===== epilogue: one thread per row (TMEM lane) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float runmax = -CUDART_INF_F, thr = -CUDART_INF_F;
+        int cnt = 0, overflow = 0;
+        float *cs = s.cand_s + row * TC_CAP;
+        int *cv = s.cand_v + row * TC_CAP;
+        for (int t = 0; t < T; ++t) {
+            const int as = t & 1;
+            mbar_wait(&s.tfull[as], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN);
+            const int vt = t * TC_BN;
+            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                if (m >= thr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int code = vt + c0 + j;
+                        if (v[j] >= thr && code < V) cand_push(v[j], code, cs, cv, cnt, overflow, runmax, thr);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.tempty[as]);
+        }
+        // exact canonical rescoring of the surviving candidates
+        float best_d = CUDART_INF_F;
+        int best_v = 0x7fffffff;
+        const float zz = s.zz[row];
+        if (!overflow) {
+            for (int e = 0; e < cnt; ++e) {
+                if (cs[e] < thr) continue;
+                const int code = cv[e];
+                const float *en = En + (size_t)code * C;
+                float dot = 0.f;
+                for (int k = 0; k < C; ++k)
+                    dot = fmaf(*(const float *)((const uint8_t *)s.A + sw128_off(row, k, TC_BM)), en[k], dot);
+                float d = fmaf(-2.0f, dot, zz + ee[code]);
+                if (d < best_d || (d == best_d && code < best_v)) { best_d = d; best_v = code; }
+            }
+        } else {
+            for (int code = 0; code < V; ++code) {   // pathological rows (> CAP near-ties): exact scan
+                const float *en = En + (size_t)code * C;
+                float dot = 0.f;
+                for (int k = 0; k < C; ++k)
+                    dot = fmaf(*(const float *)((const uint8_t *)s.A + sw128_off(row, k, TC_BM)), en[k], dot);
+                float d = fmaf(-2.0f, dot, zz + ee[code]);
+                if (d < best_d) { best_d = d; best_v = code; }
+            }
+        }
+        s.idx[row] = best_v;
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+    // ---- common epilogue: gather raw code, renormalise (xqgan_model.py:769-771), STE value, MSE, histogram
+    float sq = 0.f;
+    if (tid < TC_BM && row0 + tid < N) {
+        const int n = row0 + tid;
+        int v = s.idx[tid];
+        if (v < 0 || v >= V) v = 0;
+        const float *e = E + (size_t)v * C;
+        float ss = 0.f;
+        for (int k = 0; k < C; ++k) { float x = e[k]; ss = fmaf(x, x, ss); }
+        const float den = fmaxf(sqrtf(ss), XQ_EPS);
+        const int b = n / HW, pp = n - b * HW;
+        float *op = out + (size_t)b * C * HW + pp;
+        for (int k = 0; k < C; ++k) {
+            float qv = e[k] / den;
+            float zn = *(const float *)((const uint8_t *)s.A + sw128_off(tid, k, TC_BM));
+            float df = qv - zn;
+            sq = fmaf(df, df, sq);
+            op[(size_t)k * HW] = ste_value ? zn + df : qv;
+        }
+        idx_out[n] = (int64_t)v;
+        if (hist) atomicAdd(hist + v, 1.0f);
+    }
+    sq = block_sum(sq, s.red);
+    if (tid == 0 && partial) partial[blockIdx.x] = sq;
+}
+
+// row-major normalised codebook En[Vpad][C] (+ ee[Vpad]); padded rows are zero
+__global__ void codebook_prep_rowmajor_kernel(const float *__restrict__ E, int V, int C, int Vpad, float *__restrict__ En,
+                                              float *__restrict__ ee) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= Vpad) return;
+    if (v >= V) {
+        for (int k = 0; k < C; ++k) En[(size_t)v * C + k] = 0.f;
+        ee[v] = CUDART_INF_F;
+        return;
+    }
+    const float *e = E + (size_t)v * C;
+    float ss = 0.f;
+    for (int k = 0; k < C; ++k) ss = fmaf(e[k], e[k], ss);
+    float den = fmaxf(sqrtf(ss), XQ_EPS);
+    float s2 = 0.f;
+    for (int k = 0; k < C; ++k) {
+        float x = e[k] / den;
+        En[(size_t)v * C + k] = x;
+        s2 = fmaf(x, x, s2);
+    }
+    ee[v] = s2;
+}
+
+__global__ void finalize_mse_tc_kernel(const float *__restrict__ partial, int n, double inv_count, float beta,
+                                       float *__restrict__ loss) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) acc += (double)partial[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) {
+        float mse = (float)(acc * inv_count);
+        loss[0] = mse;
+        loss[1] = beta * mse;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;   // resolved once per process (a function pointer, not kernel state)
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+size_t vq_tc_workspace_bytes(int B, int C, int HW, int V) {
+    size_t Vp = ((size_t)V + TC_BN - 1) / TC_BN * TC_BN;
+    size_t ctas = ((size_t)B * HW + TC_BM - 1) / TC_BM;
+    return align_up(sizeof(float) * Vp * C, 1024) + align_up(sizeof(float) * Vp, 256) + align_up(sizeof(float) * ctas, 256);
+}
+
+bool vq_tc_supported(int C, int V, int codebook_norm) {
+    return codebook_norm && (C == 32 || C == 64) && V >= 1;
+}
+
+// returns XQ_OK, or an error; XQ_ERR_UNSUPPORTED lets the caller fall back to the exact CUDA-core kernel
+int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, int ste_value, float beta, int64_t *idx,
+                  float *out, float *loss, float *hist, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!vq_tc_supported(C, V, 1)) return XQ_ERR_UNSUPPORTED;
+    if (workspace_bytes < vq_tc_workspace_bytes(B, C, HW, V)) return XQ_ERR_WORKSPACE;
+    if (((uintptr_t)workspace & 127) != 0) return XQ_ERR_UNSUPPORTED;   // TMA global address alignment
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return XQ_ERR_UNSUPPORTED;
+    const int Vp = (V + TC_BN - 1) / TC_BN * TC_BN;
+    const int N = B * HW;
+    char *ws = (char *)workspace;
+    float *En = (float *)ws;
+    ws += align_up(sizeof(float) * (size_t)Vp * C, 1024);
+    float *ee = (float *)ws;
+    ws += align_up(sizeof(float) * (size_t)Vp, 256);
+    float *partial = (float *)ws;
+    const int nstage = (C == 32) ? 4 : 2;
+    const size_t smem = tc_smem_bytes(C, nstage);
+    if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
+
+    CUtensorMap tm;
+    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)Vp};
+    cuuint64_t gstr[1] = {(cuuint64_t)C * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)TC_BN};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)En, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return XQ_ERR_UNSUPPORTED;
+
+    codebook_prep_rowmajor_kernel<<<(Vp + 127) / 128, 128, 0, stream>>>(E, V, C, Vp, En, ee);
+    XQ_LAUNCH_CHECK("codebook_prep_rowmajor_kernel");
+    XQ_CUDA_TRY(cudaFuncSetAttribute(vq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas = (N + TC_BM - 1) / TC_BM;
+    vq_search_tc_kernel<<<ctas, TC_THREADS, smem, stream>>>(tm, z, E, En, ee, N, C, HW, V, Vp, nstage, ste_value, idx, out,
+                                                           loss ? partial : nullptr, hist);
+    XQ_LAUNCH_CHECK("vq_search_tc_kernel");
+    if (loss) {
+        finalize_mse_tc_kernel<<<1, 32, 0, stream>>>(partial, ctas, 1.0 / ((double)N * (double)C), beta, loss);
+        XQ_LAUNCH_CHECK("finalize_mse_tc_kernel");
+    }
+    return XQ_OK;
+}
+
+}  // namespace xq

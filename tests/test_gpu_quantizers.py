@@ -437,3 +437,50 @@ def test_msbr_full_size_properties():
                          pn, using_znorm=True, dropout=np.array([11, 11]), scaler=npy(q.scaler))
     for si in range(len(pn)):
         np.testing.assert_array_equal(npy(idx_list[si][:2]), fwd["idx"][si])
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 screening + exact rescoring == exact CUDA-core kernel == oracle (bit for bit)
+# ------------------------------------------------------------------------------------------
+def _run_vq_algo(algo, z, E):
+    import os
+    from imagefolder_b200 import ops
+    old = os.environ.get("XQ_VQ_ALGO")
+    os.environ["XQ_VQ_ALGO"] = algo
+    try:
+        out, vq, commit, idx, hist = ops.vq_forward(z, E, 0.25, True, True)
+        q, idx2 = ops.vq_lookup(z, E, True)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("XQ_VQ_ALGO", None)
+        else:
+            os.environ["XQ_VQ_ALGO"] = old
+    return out, vq, idx, hist, q, idx2
+
+
+@pytest.mark.parametrize("B,C,hw,V,init", [(2, 32, 16, 1000, "randn"), (1, 32, 1, 5, "randn"), (5, 64, 5, 4096, "ref"),
+                                           (3, 32, 7, 300, "dup"), (64, 32, 16, 8192, "ref"), (256, 32, 16, 8192, "randn"),
+                                           (128, 64, 16, 4096, "randn"), (128, 32, 16, 16384, "ref")])
+def test_vq_tcgen05_path_is_bit_identical(B, C, hw, V, init):
+    torch.manual_seed(B * 7 + V)
+    z = torch.randn(B, C, hw, hw, device="cuda")
+    if init == "ref":
+        E = torch.empty(V, C, device="cuda").uniform_(-1.0 / V, 1.0 / V)
+        E = torch.nn.functional.normalize(E, dim=-1)
+    else:
+        E = torch.randn(V, C, device="cuda") * 0.3
+        if init == "dup":                      # exact ties: duplicated rows, lower index must win
+            E = torch.cat([E[: V // 3]] * 3 + [E[: V - 3 * (V // 3)]], 0)
+    o_e, vq_e, idx_e, hist_e, q_e, idx2_e = _run_vq_algo("exact", z, E)
+    o_t, vq_t, idx_t, hist_t, q_t, idx2_t = _run_vq_algo("tc", z, E)
+    assert torch.equal(idx_t, idx_e), f"{int((idx_t != idx_e).sum())} index mismatches"
+    assert torch.equal(idx2_t, idx_e)
+    assert torch.equal(o_t, o_e) and torch.equal(q_t, q_e) and torch.equal(hist_t, hist_e)
+    assert abs(float(vq_t) - float(vq_e)) <= 1e-6 * float(vq_e)
+    if init == "dup":
+        assert int(idx_t.max()) < V // 3
+    # and against the CPU oracle on a slice
+    nb = min(B, 4)
+    fwd = xo.vq_forward(npy(z[:nb]), npy(E))
+    np.testing.assert_array_equal(npy(idx_t[: nb * hw * hw]), fwd["idx"])
