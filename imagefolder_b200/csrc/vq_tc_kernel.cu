@@ -5,11 +5,12 @@
 //   screening   the -2<z,c> inner products of a 128-row x 256-code tile are computed by ONE thread issuing
 //               tcgen05.mma.kind::tf32 (operands in 128B-swizzled shared memory: rows written by the CTA,
 //               code tiles streamed by TMA), accumulators in TMEM (2 x 256 columns, double buffered);
-//   epilogue    4 warps read their TMEM lanes with tcgen05.ld and keep, per row, the few codes whose
-//               approximate score is within W of the running maximum;
-//   rescoring   only those candidates (1.1 per row on average) are re-scored with the canonical fp32
-//               arithmetic (fmaf chain, d = (zz+ee) - 2 dot, first index on ties) -> the index equals the
-//               exact kernel's and the oracle's, because the true argmin is provably among the candidates.
+//   epilogue    4 warps read their TMEM lanes with tcgen05.ld (32 columns at a time), take the maximum of each
+//               32-code group with FMNMX3 trees and remember, per row, the few groups whose maximum is
+//               within W of the running maximum (a push is ~10 instructions; no per-element scan);
+//   rescoring   only the codes of those groups (1.1 groups per row on average) are re-scored with the
+//               canonical fp32 arithmetic (fmaf chain, d = (zz+ee) - 2 dot, first index on ties) -> the index
+//               equals the exact kernel's and the oracle's: the true argmin provably lies in a kept group.
 //
 // Error bound (codebook_norm=1, |z| = |c| = 1 up to 1e-6): TF32 operands carry <= 2^-10 relative error
 // each, so |dot_tf32 - dot| <= 2^-9 * sum|z_k c_k| <= 1.96e-3.  We use eps = 2.5e-3 and keep every code with
@@ -19,15 +20,16 @@
 // (TMEM lane quadrant = warp_id % 4).  Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA),
 // tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "xq_common.cuh"
 
 namespace xq {
 
 constexpr int TC_BM = 128;       // rows per CTA  (UMMA M)
-constexpr int TC_BN = 256;       // codes per tile (UMMA N)
+constexpr int TC_BN = 128;       // codes per tile (UMMA N); 2 accumulator stages = 256 TMEM columns -> 2 CTAs / SM
 constexpr int TC_THREADS = 192;
-constexpr int TC_CAP = 16;       // candidate slots per row
+constexpr int TC_CAP = 24;       // candidate-group slots per row
 constexpr float TC_EPS = 2.5e-3f;
 constexpr float TC_W = 2.0f * TC_EPS + 2e-6f;
 
@@ -87,10 +89,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, 8-row atoms 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -113,18 +115,16 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows_per_chunk
     return (uint32_t)(kc * rows_per_chunk * 128 + row * 128 + (((kk >> 2) ^ (row & 7)) << 4) + ((kk & 3) << 2));
 }
 
-// slow path of the epilogue (a handful of calls per row): remember a candidate, compacting the list when full
-__device__ __noinline__ void cand_push(float score, int code, float *cs, int *cv, int &cnt, int &overflow,
-                                       float &runmax, float &thr) {
-    if (cnt == TC_CAP) {  // drop entries that fell below the threshold since they were stored
+// remember a candidate group (score = its maximum, id = group index); compacts the list when it is full
+__device__ __forceinline__ void cand_push(float score, int gid, float *cs, int *cv, int &cnt, int &overflow, float thr) {
+    if (cnt == TC_CAP) {  // drop groups that fell below the threshold since they were stored
         int w = 0;
         for (int e = 0; e < TC_CAP; ++e)
             if (cs[e] >= thr) { cs[w] = cs[e]; cv[w] = cv[e]; ++w; }
         cnt = w;
     }
-    if (cnt < TC_CAP) { cs[cnt] = score; cv[cnt] = code; ++cnt; }
+    if (cnt < TC_CAP) { cs[cnt] = score; cv[cnt] = gid; ++cnt; }
     else overflow = 1;
-    if (score > runmax) { runmax = score; thr = runmax - TC_W; }
 }
 
 struct TcSmem {
@@ -148,12 +148,16 @@ static size_t tc_smem_bytes(int C, int nstage) {
     return b;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__restrict__ z, const float *__restrict__ E,
                     const float *__restrict__ En, const float *__restrict__ ee, int N, int C, int HW, int V, int Vpad,
                     int nstage, int ste_value, int64_t *__restrict__ idx_out, float *__restrict__ out,
-                    float *__restrict__ partial, float *__restrict__ hist) {
+                    float *__restrict__ partial, float *__restrict__ hist, long long *__restrict__ dbg) {
     extern __shared__ uint8_t smem_raw[];
+    // dbg (optional, CTA 0 only): [0] start, [1] after prologue; per tile t: [8+4t+0] mma waited tempty,
+    // [+1] mma waited full, [+2] mma issued+committed, [+3] epilogue warp 2 done with tile
+    const bool trace = dbg && blockIdx.x == 0;
+    if (trace && threadIdx.x == 0) dbg[0] = clock64();
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     TcSmem s;
     s.A = (float *)base;
@@ -182,26 +186,31 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_ptr)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_ptr)), "r"(2 * TC_BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // rows: normalise (canonical chain) and store into the swizzled A operand; threads 0..127 own one row each
-    if (tid < TC_BM) {
-        const int n = row0 + tid;
-        float den = 1.f, zz = 0.f;
+    // rows: coalesced load of the raw NCHW tile into the swizzled A operand (consecutive threads = consecutive
+    // rows of one channel), then one thread per row normalises in place with the canonical chain
+    for (int i = tid; i < C * TC_BM; i += TC_THREADS) {
+        const int k = i / TC_BM, r = i - k * TC_BM;
+        const int n = row0 + r;
+        float x = 0.f;
         if (n < N) {
             const int b = n / HW, pp = n - b * HW;
-            const float *zp = z + (size_t)b * C * HW + pp;
-            float ss = 0.f;
-            for (int k = 0; k < C; ++k) { float x = zp[(size_t)k * HW]; ss = fmaf(x, x, ss); }
-            den = fmaxf(sqrtf(ss), XQ_EPS);
-            for (int k = 0; k < C; ++k) {
-                float x = zp[(size_t)k * HW] / den;
-                zz = fmaf(x, x, zz);
-                *(float *)((uint8_t *)s.A + sw128_off(tid, k, TC_BM)) = x;
-            }
-        } else {
-            for (int k = 0; k < C; ++k) *(float *)((uint8_t *)s.A + sw128_off(tid, k, TC_BM)) = 0.f;
+            x = z[((size_t)b * C + k) * HW + pp];
+        }
+        *(float *)((uint8_t *)s.A + sw128_off(r, k, TC_BM)) = x;
+    }
+    __syncthreads();
+    if (tid < TC_BM) {
+        float ss = 0.f, zz = 0.f;
+        for (int k = 0; k < C; ++k) { float x = *(const float *)((const uint8_t *)s.A + sw128_off(tid, k, TC_BM)); ss = fmaf(x, x, ss); }
+        const float den = fmaxf(sqrtf(ss), XQ_EPS);
+        for (int k = 0; k < C; ++k) {
+            float *pa = (float *)((uint8_t *)s.A + sw128_off(tid, k, TC_BM));
+            float x = *pa / den;
+            zz = fmaf(x, x, zz);
+            *pa = x;
         }
         s.zz[tid] = zz;
     }
@@ -210,6 +219,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s.tmem_ptr;
+    if (trace && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -231,7 +241,9 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
             for (int t = 0; t < T; ++t) {
                 const int st = t % nstage, as = t & 1;
                 mbar_wait(&s.tempty[as], ((t >> 1) & 1) ^ 1);
+                if (trace && t < 60) dbg[8 + 4 * t + 0] = clock64();
                 mbar_wait(&s.full[st], (t / nstage) & 1);
+                if (trace && t < 60) dbg[8 + 4 * t + 1] = clock64();
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(s.B + (size_t)st * TC_BN * C);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
@@ -245,6 +257,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
                 }
                 umma_commit(&s.empty[st]);    // smem stage free once these MMAs retire
                 umma_commit(&s.tfull[as]);    // accumulator ready
+                if (trace && t < 60) dbg[8 + 4 * t + 2] = clock64();
             }
         }
     } else {
@@ -261,48 +274,74 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN);
             const int vt = t * TC_BN;
-            for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                float m = v[0];
+            float v[TC_BN / 32][32];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-                if (m >= thr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int code = vt + c0 + j;
-                        if (v[j] >= thr && code < V) cand_push(v[j], code, cs, cv, cnt, overflow, runmax, thr);
-                    }
-                }
-            }
+            for (int g = 0; g < TC_BN / 32; ++g) tmem_ld32(taddr + g * 32, v[g]);   // issue all loads, wait once
+            tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s.tempty[as]);
+            if (lane == 0) mbar_arrive(&s.tempty[as]);     // the accumulator stage is free as soon as it is in registers
+#pragma unroll
+            for (int g = 0; g < TC_BN / 32; ++g) {
+                float m = v[g][0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[g][j]);
+                if (m >= thr) {          // rare per row (~ln(#groups) times), cheap
+                    if (m > runmax) { runmax = m; thr = runmax - TC_W; }
+                    cand_push(m, (vt >> 5) + g, cs, cv, cnt, overflow, thr);
+                }
+            }
+
+            if (trace && warp == 2 && lane == 0 && t < 60) dbg[8 + 4 * t + 3] = clock64();
         }
-        // exact canonical rescoring of the surviving candidates
+        if (trace && warp == 2 && lane == 0) dbg[2] = clock64();
+        // exact canonical rescoring, warp-cooperative: for every (row, candidate group) of this warp, lane j
+        // scores code j of the group against the row (row values broadcast from smem, the 32 code rows are one
+        // contiguous 32*C*4-byte block of En), then a (d, code) lexicographic warp-argmin picks the winner.
         float best_d = CUDART_INF_F;
         int best_v = 0x7fffffff;
-        const float zz = s.zz[row];
-        if (!overflow) {
-            for (int e = 0; e < cnt; ++e) {
-                if (cs[e] < thr) continue;
-                const int code = cv[e];
-                const float *en = En + (size_t)code * C;
-                float dot = 0.f;
-                for (int k = 0; k < C; ++k)
-                    dot = fmaf(*(const float *)((const uint8_t *)s.A + sw128_off(row, k, TC_BM)), en[k], dot);
-                float d = fmaf(-2.0f, dot, zz + ee[code]);
-                if (d < best_d || (d == best_d && code < best_v)) { best_d = d; best_v = code; }
+        const unsigned any_overflow = __ballot_sync(0xffffffffu, overflow != 0);
+        for (int r = 0; r < 32; ++r) {
+            const int rrow = q * 32 + r;
+            const int rcnt = __shfl_sync(0xffffffffu, cnt, r);
+            const float rthr = __shfl_sync(0xffffffffu, thr, r);
+            const float rzz = s.zz[rrow];
+            float rb_d = CUDART_INF_F;
+            int rb_v = 0x7fffffff;
+            const int ngroups = ((any_overflow >> r) & 1u) ? (V + 31) / 32 : rcnt;   // overflow: scan every group
+            for (int e = 0; e < ngroups; ++e) {
+                int gid;
+                if ((any_overflow >> r) & 1u) gid = e;
+                else {
+                    if (s.cand_s[rrow * TC_CAP + e] < rthr) continue;     // warp-uniform
+                    gid = s.cand_v[rrow * TC_CAP + e];
+                }
+                const int code = (gid << 5) + lane;
+                float d = CUDART_INF_F;
+                if (code < V) {
+                    const float4 *en4 = reinterpret_cast<const float4 *>(En + (size_t)code * C);
+                    float dot = 0.f;
+                    for (int k4 = 0; k4 < C / 4; ++k4) {
+                        float4 ev = en4[k4];
+                        // A(rrow, 4*k4 .. 4*k4+3) is one 16-byte chunk of the swizzled operand (broadcast read)
+                        const float4 av = *reinterpret_cast<const float4 *>((const uint8_t *)s.A + sw128_off(rrow, 4 * k4, TC_BM));
+                        dot = fmaf(av.x, ev.x, dot);
+                        dot = fmaf(av.y, ev.y, dot);
+                        dot = fmaf(av.z, ev.z, dot);
+                        dot = fmaf(av.w, ev.w, dot);
+                    }
+                    d = fmaf(-2.0f, dot, rzz + ee[code]);
+                }
+                int cv_ = code;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float od = __shfl_xor_sync(0xffffffffu, d, o);
+                    int oc = __shfl_xor_sync(0xffffffffu, cv_, o);
+                    if (od < d || (od == d && oc < cv_)) { d = od; cv_ = oc; }
+                }
+                if (d < rb_d || (d == rb_d && cv_ < rb_v)) { rb_d = d; rb_v = cv_; }
             }
-        } else {
-            for (int code = 0; code < V; ++code) {   // pathological rows (> CAP near-ties): exact scan
-                const float *en = En + (size_t)code * C;
-                float dot = 0.f;
-                for (int k = 0; k < C; ++k)
-                    dot = fmaf(*(const float *)((const uint8_t *)s.A + sw128_off(row, k, TC_BM)), en[k], dot);
-                float d = fmaf(-2.0f, dot, zz + ee[code]);
-                if (d < best_d) { best_d = d; best_v = code; }
-            }
+            if (lane == r) { best_d = rb_d; best_v = rb_v; }
         }
         s.idx[row] = best_v;
     }
@@ -311,7 +350,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     __syncthreads();
     tc_fence_after();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN));
     }
     // ---- common epilogue: gather raw code, renormalise (xqgan_model.py:769-771), STE value, MSE, histogram
     float sq = 0.f;
@@ -337,6 +376,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     }
     sq = block_sum(sq, s.red);
     if (tid == 0 && partial) partial[blockIdx.x] = sq;
+    if (trace && tid == 0) dbg[3] = clock64();
 }
 
 // row-major normalised codebook En[Vpad][C] (+ ee[Vpad]); padded rows are zero
@@ -416,7 +456,7 @@ int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, i
     float *ee = (float *)ws;
     ws += align_up(sizeof(float) * (size_t)Vp, 256);
     float *partial = (float *)ws;
-    const int nstage = (C == 32) ? 4 : 2;
+    const int nstage = (C == 32) ? 4 : 3;
     const size_t smem = tc_smem_bytes(C, nstage);
     if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
 
@@ -434,8 +474,10 @@ int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, i
     XQ_LAUNCH_CHECK("codebook_prep_rowmajor_kernel");
     XQ_CUDA_TRY(cudaFuncSetAttribute(vq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas = (N + TC_BM - 1) / TC_BM;
+    long long *dbg = nullptr;
+    if (const char *e = getenv("XQ_VQ_TC_TRACE")) dbg = (long long *)strtoull(e, nullptr, 0);  // device pointer (dev tool)
     vq_search_tc_kernel<<<ctas, TC_THREADS, smem, stream>>>(tm, z, E, En, ee, N, C, HW, V, Vp, nstage, ste_value, idx, out,
-                                                           loss ? partial : nullptr, hist);
+                                                           loss ? partial : nullptr, hist, dbg);
     XQ_LAUNCH_CHECK("vq_search_tc_kernel");
     if (loss) {
         finalize_mse_tc_kernel<<<1, 32, 0, stream>>>(partial, ctas, 1.0 / ((double)N * (double)C), beta, loss);

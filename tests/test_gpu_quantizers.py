@@ -428,7 +428,9 @@ def test_msbr_full_size_properties():
     assert torch.isfinite(f.grad).all()
     idx_list = q.f_to_idxBl_or_fhat(f.detach(), to_fhat=False, v_patch_nums=pn)
     for si, p in enumerate(pn):
-        assert float(q.ema_vocab_hit_SV[si].sum()) == 128 * p * p
+        # histogram is a partition of the 128*p*p tokens; scale 0 copies it, later scales blend 0.9/0.1 (record_hit)
+        expect = 128 * p * p * (1.0 if si == 0 else 0.1)
+        assert abs(float(q.ema_vocab_hit_SV[si].sum()) - expect) < 1e-3 * expect
         assert int(idx_list[si].max()) < 16384 and int(idx_list[si].min()) >= 0
     fh = q.f_to_idxBl_or_fhat(f.detach(), to_fhat=True, v_patch_nums=pn)
     assert torch.equal(q.idx_to_fhat(idx_list), fh[-1])
