@@ -16,7 +16,8 @@
 
 namespace xq {
 
-constexpr int MS_THREADS = 256;
+constexpr int MS_THREADS = 256;       // forward / decode (the search tiling assumes 16 x 16 threads)
+constexpr int MS_BWD_THREADS = 512;   // backward: no search, only latency-bound conv / pooling work -> more warps
 constexpr int MS_TILE_V = 128;
 
 struct MsArgs {
@@ -50,6 +51,7 @@ struct MsSmem {
     float *rbest;                   // [8 warps][16] cross-warp argmin scratch
     int *ridx;                      // [8][16]
     int *idx;                       // [RP]
+    float *w;                       // Phi weights + bias of the current scale [C*C*9 + C]
 };
 // row pitch of the k-major row buffer: padded to the 128-row search block so that tile reads stay in bounds
 __host__ __device__ inline int ms_rp(int H, int W) { return (H * W + 127) / 128 * 128; }
@@ -59,6 +61,7 @@ __host__ __device__ inline size_t ms_fwd_smem_floats(int C, int H, int W, int SN
     if (search) n += (size_t)2 * C * MS_TILE_V + 2 * MS_TILE_V;
     n += 4 * (size_t)(H + W) * 2;  // wy,wx,iy,ix
     n += XQ_MAX_SCALES + 32 + 8 * 16 * 2 + rp + 16;
+    n += (size_t)C * C * 9 + C;   // staged Phi weights
     return n;
 }
 __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, bool search) {
@@ -81,6 +84,7 @@ __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, boo
     s.rbest = p; p += 8 * 16;
     s.ridx = (int *)p; p += 8 * 16;
     s.idx = (int *)p; p += rp;
+    s.w = p; p += (size_t)C * C * 9 + C;
     return s;
 }
 
@@ -89,7 +93,7 @@ __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, boo
 // area pool rest[C][H][W] -> rows k-major [C][RP] (row r = oy*P+ox); P==H -> copy.
 __device__ __forceinline__ void ms_area_pool(const float *rest, float *rows, int C, int H, int W, int P, int RP) {
     const int R = P * P;
-    for (int i = threadIdx.x; i < C * R; i += MS_THREADS) {
+    for (int i = threadIdx.x; i < C * R; i += blockDim.x) {
         int c = i / R, r = i - c * R;
         int oy = r / P, ox = r - oy * P;
         const float *plane = rest + (size_t)c * H * W;
@@ -110,7 +114,7 @@ __device__ __forceinline__ void ms_area_pool(const float *rest, float *rows, int
 
 // rows (k-major) -> normalise each row in place (ZNORM) and/or compute zz (L2).  zz_out may alias red-free smem.
 __device__ __forceinline__ void ms_rows_prepare(float *rows, int C, int R, int RP, bool normalise, float *zz_out) {
-    for (int r = threadIdx.x; r < R; r += MS_THREADS) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
         if (normalise) {
             float ss = 0.f;
             for (int k = 0; k < C; ++k) { float x = rows[k * RP + r]; ss = fmaf(x, x, ss); }
@@ -271,7 +275,7 @@ __device__ void ms_search_block(const MsSmem &s, const float *__restrict__ EnT, 
 // gather raw code rows (or +-scaler for BSQ) into rows (k-major), reusing the rows buffer
 __device__ __forceinline__ void ms_gather(const MsSmem &s, const float *__restrict__ E, int C, int R, int RP, int V,
                                           bool bsq, float scaler) {
-    for (int i = threadIdx.x; i < C * R; i += MS_THREADS) {
+    for (int i = threadIdx.x; i < C * R; i += blockDim.x) {
         int r = i / C, k = i - r * C;
         int v = s.idx[r];
         float val;
@@ -282,7 +286,7 @@ __device__ __forceinline__ void ms_gather(const MsSmem &s, const float *__restri
 }
 
 __device__ __forceinline__ void ms_cubic_tables(const MsSmem &s, int P, int H, int W) {
-    for (int d = threadIdx.x; d < H + W; d += MS_THREADS) {
+    for (int d = threadIdx.x; d < H + W; d += blockDim.x) {
         int idx[4];
         float w[4];
         if (d < H) {
@@ -299,7 +303,7 @@ __device__ __forceinline__ void ms_cubic_tables(const MsSmem &s, int P, int H, i
 // u[c][y][x] = bicubic(gath[P,P,c]) ; P==H -> copy.  gath is k-major rows[c][RP].
 __device__ __forceinline__ void ms_bicubic_up(const MsSmem &s, int C, int H, int W, int P, int RP) {
     const int HW = H * W;
-    for (int i = threadIdx.x; i < C * HW; i += MS_THREADS) {
+    for (int i = threadIdx.x; i < C * HW; i += blockDim.x) {
         int c = i / HW, p = i - c * HW;
         int y = p / W, x = p - y * W;
         const float *g = s.rows + c * RP;
@@ -341,7 +345,7 @@ __device__ __forceinline__ void ms_phi_point(const float *u, const float *__rest
                 float uv = plane[yy * W + xx];
 #pragma unroll
                 for (int j = 0; j < COB; ++j)
-                    acc[j] = fmaf(__ldg(w + ((size_t)(co0 + j) * C + ci) * 9 + ky * 3 + kx), uv, acc[j]);
+                    acc[j] = fmaf(w[((size_t)(co0 + j) * C + ci) * 9 + ky * 3 + kx], uv, acc[j]);
             }
         }
     }
@@ -357,7 +361,7 @@ template <int COB, typename F>
 __device__ __forceinline__ void ms_phi_foreach(const float *u, const float *w, const float *bias, int C, int H, int W,
                                                float r, F f) {
     const int HW = H * W, G = C / COB;
-    for (int i = threadIdx.x; i < G * HW; i += MS_THREADS) {
+    for (int i = threadIdx.x; i < G * HW; i += blockDim.x) {
         int g = i / HW, p = i - g * HW;
         int y = p / W, x = p - y * W;
         float h[COB];
@@ -379,7 +383,7 @@ __device__ __forceinline__ void ms_phi_dispatch(const float *u, const float *w, 
 }
 
 __device__ __forceinline__ void ms_ratios(const MsSmem &s, const float *nq, int B, int SN) {
-    for (int si = threadIdx.x; si < SN; si += MS_THREADS) {
+    for (int si = threadIdx.x; si < SN; si += blockDim.x) {
         float cnt = 0.f;
         if (nq) { for (int b = 0; b < B; ++b) cnt += ((float)si < nq[b]) ? 1.f : 0.f; }
         else cnt = (float)B;
@@ -416,8 +420,8 @@ ms_forward_kernel(const MsArgs a) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const float *fb = a.fn + (size_t)b * CHW;
 
-    for (int i = tid; i < CHW; i += MS_THREADS) { s.rest[i] = fb[i]; s.fhat[i] = 0.f; }
-    for (int i = tid; i < C * RP; i += MS_THREADS) s.rows[i] = 0.f;
+    for (int i = tid; i < CHW; i += blockDim.x) { s.rest[i] = fb[i]; s.fhat[i] = 0.f; }
+    for (int i = tid; i < C * RP; i += blockDim.x) s.rows[i] = 0.f;
     if (a.with_losses) ms_ratios(s, a.nq, d.B, d.SN);
     __syncthreads();
     const float nq_b = (a.with_losses && a.nq) ? a.nq[b] : 3.0e38f;
@@ -425,6 +429,7 @@ ms_forward_kernel(const MsArgs a) {
     int64_t off = 0;
     float *zz_s = s.rbest;  // R<=16 path keeps zz here?  no: rbest is written by the reduction -> use u as scratch
     zz_s = s.u;             // u is free during the search phase
+    int cur_phi = -1;
 
     for (int si = 0; si < d.SN; ++si) {
         const int P = d.patch_nums[si], R = P * P;
@@ -432,7 +437,7 @@ ms_forward_kernel(const MsArgs a) {
         if (P != H || P != W) ms_cubic_tables(s, P, H, W);
         __syncthreads();
         if (bsq) {
-            for (int r = tid; r < R; r += MS_THREADS) {
+            for (int r = tid; r < R; r += blockDim.x) {
                 int code = 0;
                 for (int k = 0; k < C; ++k) code |= (s.rows[k * RP + r] > 0.f ? 1 : 0) << k;
                 s.idx[r] = code;
@@ -444,7 +449,7 @@ ms_forward_kernel(const MsArgs a) {
             ms_search(s, a, R, RP, zz_s);
         }
         // indices out + histogram
-        for (int r = tid; r < R; r += MS_THREADS) {
+        for (int r = tid; r < R; r += blockDim.x) {
             int v = s.idx[r];
             a.idx_all[off + (int64_t)b * R + r] = (int64_t)v;
             if (a.hist) atomicAdd(a.hist + (size_t)si * d.V + v, 1.0f);
@@ -455,11 +460,18 @@ ms_forward_kernel(const MsArgs a) {
         __syncthreads();
         if (bsq && a.Fprev01 && b < 2) {
             float *dst = a.Fprev01 + ((size_t)si * 2 + b) * CHW;
-            for (int i = tid; i < CHW; i += MS_THREADS) dst[i] = s.fhat[i];
+            for (int i = tid; i < CHW; i += blockDim.x) dst[i] = s.fhat[i];
         }
         const int kphi = d.K > 0 ? d.phi_map[si] : -1;
-        const float *w = kphi >= 0 ? a.phi_w + (size_t)kphi * C * C * 9 : nullptr;
-        const float *bias = kphi >= 0 ? a.phi_b + (size_t)kphi * C : nullptr;
+        if (kphi >= 0 && kphi != cur_phi) {   // stage this Phi's weights + bias in shared memory
+            const float *gw = a.phi_w + (size_t)kphi * C * C * 9, *gb = a.phi_b + (size_t)kphi * C;
+            for (int i = tid; i < C * C * 9; i += blockDim.x) s.w[i] = gw[i];
+            for (int i = tid; i < C; i += blockDim.x) s.w[C * C * 9 + i] = gb[i];
+            cur_phi = kphi;
+            __syncthreads();
+        }
+        const float *w = kphi >= 0 ? s.w : nullptr;
+        const float *bias = kphi >= 0 ? s.w + C * C * 9 : nullptr;
         const bool m = !a.with_losses || ((float)si < nq_b);
         float sq = 0.f;
         float *fs = a.fhat_scales ? a.fhat_scales + ((size_t)si * d.B + b) * CHW : nullptr;
@@ -476,7 +488,7 @@ ms_forward_kernel(const MsArgs a) {
         __syncthreads();
     }
     // epilogue: out, saved F_last, loss partial
-    for (int i = tid; i < CHW; i += MS_THREADS) {
+    for (int i = tid; i < CHW; i += blockDim.x) {
         float F = s.fhat[i], fv = fb[i];
         a.out[(size_t)b * CHW + i] = a.with_losses ? (F - fv) + fv : F;
         if (a.F_last) a.F_last[(size_t)b * CHW + i] = F;
@@ -628,7 +640,7 @@ struct MsBwdArgs {
 };
 
 struct MsBwdSmem {
-    float *F, *S, *u, *dh, *du, *rows, *tmp;
+    float *F, *S, *u, *dh, *du, *rows, *tmp, *w;   // w: Phi weights + bias of the current scale
     float *wy, *wx;
     int *iy, *ix;
     float *My, *Mx;  // dense [H][P], [W][P]
@@ -638,7 +650,7 @@ struct MsBwdSmem {
 __host__ __device__ inline size_t ms_bwd_smem_floats(int C, int H, int W) {
     size_t chw = (size_t)C * H * W, rp = (size_t)ms_rp(H, W);
     return 5 * chw + (size_t)C * rp + chw /*tmp*/ + 8 * (size_t)(H + W) + (size_t)H * H + (size_t)W * W +
-           XQ_MAX_SCALES + rp + 16;
+           XQ_MAX_SCALES + rp + 16 + (size_t)C * C * 9 + C;
 }
 __device__ __forceinline__ MsBwdSmem ms_bwd_carve(float *base, int C, int H, int W) {
     MsBwdSmem s;
@@ -659,10 +671,11 @@ __device__ __forceinline__ MsBwdSmem ms_bwd_carve(float *base, int C, int H, int
     s.Mx = p; p += (size_t)W * W;
     s.ratio = p; p += XQ_MAX_SCALES;
     s.idx = (int *)p; p += rp;
+    s.w = p; p += (size_t)C * C * 9 + C;
     return s;
 }
 
-__global__ void __launch_bounds__(MS_THREADS)
+__global__ void __launch_bounds__(MS_BWD_THREADS)
 ms_backward_kernel(const MsBwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     const xq_ms_desc &d = a.d;
@@ -680,7 +693,7 @@ ms_backward_kernel(const MsBwdArgs a) {
     const float r = d.resi_ratio;
 
     ms_ratios(fs, a.nq, d.B, SN);
-    for (int i = tid; i < CHW; i += MS_THREADS) {
+    for (int i = tid; i < CHW; i += blockDim.x) {
         s.F[i] = a.F_last[(size_t)b * CHW + i];
         s.S[i] = 0.f;
         s.tmp[i] = 0.f;
@@ -688,7 +701,7 @@ ms_backward_kernel(const MsBwdArgs a) {
     __syncthreads();
     // gf accumulates in global (each element owned by one thread): start from g_out (+ entropy grads)
     float *gfb = a.gf + (size_t)b * CHW;
-    for (int i = tid; i < CHW; i += MS_THREADS) {
+    for (int i = tid; i < CHW; i += blockDim.x) {
         float g = a.g_out ? a.g_out[(size_t)b * CHW + i] : 0.f;
         if (a.gent && b < 2) g += a.gent[(size_t)b * CHW + i];
         gfb[i] = g;
@@ -698,12 +711,13 @@ ms_backward_kernel(const MsBwdArgs a) {
     for (int si = 0; si < SN; ++si) off_end += (int64_t)d.B * d.patch_nums[si] * d.patch_nums[si];
 
     int64_t off = off_end;
+    int cur_phi = -1;
     for (int k = SN - 1; k >= 0; --k) {
         const int P = d.patch_nums[k], R = P * P;
         off -= (int64_t)d.B * R;
         const bool m = (float)k < nq_b;
         // --- recompute u_k, h_k
-        for (int rr = tid; rr < R; rr += MS_THREADS) s.idx[rr] = (int)a.idx_all[off + (int64_t)b * R + rr];
+        for (int rr = tid; rr < R; rr += blockDim.x) s.idx[rr] = (int)a.idx_all[off + (int64_t)b * R + rr];
         if (P != H || P != W) {
             ms_cubic_tables(fs, P, H, W);
         }
@@ -711,8 +725,8 @@ ms_backward_kernel(const MsBwdArgs a) {
         ms_gather(fs, a.E, C, R, RP, d.V, bsq, d.scaler[k]);
         if (P != H || P != W) {
             // dense transposes for the backward of the bicubic map
-            for (int i = tid; i < H * P; i += MS_THREADS) s.My[i] = 0.f;
-            for (int i = tid; i < W * P; i += MS_THREADS) s.Mx[i] = 0.f;
+            for (int i = tid; i < H * P; i += blockDim.x) s.My[i] = 0.f;
+            for (int i = tid; i < W * P; i += blockDim.x) s.Mx[i] = 0.f;
         }
         __syncthreads();
         if ((P != H || P != W) && tid == 0) {
@@ -722,8 +736,15 @@ ms_backward_kernel(const MsBwdArgs a) {
         ms_bicubic_up(fs, C, H, W, P, RP);
         __syncthreads();
         const int kphi = d.K > 0 ? d.phi_map[k] : -1;
-        const float *w = kphi >= 0 ? a.phi_w + (size_t)kphi * C * C * 9 : nullptr;
-        const float *bias = kphi >= 0 ? a.phi_b + (size_t)kphi * C : nullptr;
+        if (kphi >= 0 && kphi != cur_phi) {   // stage this Phi's weights + bias in shared memory (4 times per image)
+            const float *gw = a.phi_w + (size_t)kphi * C * C * 9, *gb = a.phi_b + (size_t)kphi * C;
+            for (int i = tid; i < C * C * 9; i += blockDim.x) s.w[i] = gw[i];
+            for (int i = tid; i < C; i += blockDim.x) s.w[C * C * 9 + i] = gb[i];
+            cur_phi = kphi;
+            __syncthreads();
+        }
+        const float *w = kphi >= 0 ? s.w : nullptr;
+        const float *bias = kphi >= 0 ? s.w + C * C * 9 : nullptr;
         // --- D = (F_k - f) m ; S += c_vq D ; gf += c_commit D ; dh = S m ; F <- F - h m
         const float ratio = s.ratio[k];
         const float c_vq = m ? gv * 2.0f / ((float)SN * n_all * ratio) : 0.f;
@@ -743,7 +764,7 @@ ms_backward_kernel(const MsBwdArgs a) {
         // --- Phi backward: du = (1-r) dh + r conv^T(dh) ; dW, db partials
         if (w) {
             // du
-            for (int i = tid; i < CHW; i += MS_THREADS) {
+            for (int i = tid; i < CHW; i += blockDim.x) {
                 int ci = i / HW, p = i - ci * HW;
                 int y = p / W, x = p - y * W;
                 float acc = 0.f;
@@ -758,7 +779,7 @@ ms_backward_kernel(const MsBwdArgs a) {
                         for (int kx = 0; kx < 3; ++kx) {
                             int xx = x - kx + 1;
                             if (xx < 0 || xx >= W) continue;
-                            acc = fmaf(__ldg(wk + ky * 3 + kx), dplane[yy * W + xx], acc);
+                            acc = fmaf(wk[ky * 3 + kx], dplane[yy * W + xx], acc);
                         }
                     }
                 }
@@ -768,7 +789,7 @@ ms_backward_kernel(const MsBwdArgs a) {
             if (gv != 0.f) {
                 float *dW = a.dWpart + ((size_t)b * d.K + kphi) * C * C * 9;
                 float *db = a.dbpart + ((size_t)b * d.K + kphi) * C;
-                for (int i = tid; i < C * C; i += MS_THREADS) {
+                for (int i = tid; i < C * C; i += blockDim.x) {
                     int co = i / C, ci = i - co * C;
                     float acc[9];
 #pragma unroll
@@ -793,26 +814,26 @@ ms_backward_kernel(const MsBwdArgs a) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) dW[(size_t)i * 9 + t] += r * acc[t];
                 }
-                for (int co = tid; co < C; co += MS_THREADS) {
+                for (int co = tid; co < C; co += blockDim.x) {
                     float acc = 0.f;
                     for (int p = 0; p < HW; ++p) acc += s.dh[(size_t)co * HW + p];
                     db[co] += r * acc;
                 }
             }
         } else {
-            for (int i = tid; i < CHW; i += MS_THREADS) s.du[i] = s.dh[i];
+            for (int i = tid; i < CHW; i += blockDim.x) s.du[i] = s.dh[i];
         }
         __syncthreads();
         // --- bicubic^T and scatter into gE
         if (!bsq && a.gE && gv != 0.f) {
             if (P == H && P == W) {
-                for (int i = tid; i < C * R; i += MS_THREADS) {
+                for (int i = tid; i < C * R; i += blockDim.x) {
                     int c = i / R, rr = i - c * R;
                     atomicAdd(a.gE + (size_t)s.idx[rr] * C + c, s.du[(size_t)c * HW + rr]);
                 }
             } else {
                 // tmp[c][y][q] = sum_x Mx[x][q] du[c][y][x]
-                for (int i = tid; i < C * H * P; i += MS_THREADS) {
+                for (int i = tid; i < C * H * P; i += blockDim.x) {
                     int c = i / (H * P), rem = i - c * (H * P);
                     int y = rem / P, q = rem - y * P;
                     float acc = 0.f;
@@ -820,7 +841,7 @@ ms_backward_kernel(const MsBwdArgs a) {
                     s.tmp[i] = acc;
                 }
                 __syncthreads();
-                for (int i = tid; i < C * R; i += MS_THREADS) {
+                for (int i = tid; i < C * R; i += blockDim.x) {
                     int c = i / R, rr = i - c * R;
                     int pp = rr / P, q = rr - pp * P;
                     float acc = 0.f;
@@ -835,7 +856,7 @@ ms_backward_kernel(const MsBwdArgs a) {
     if (d.channel_norm) {
         __syncthreads();
         const float *fraw = a.f + (size_t)b * CHW;
-        for (int p = tid; p < HW; p += MS_THREADS) {
+        for (int p = tid; p < HW; p += blockDim.x) {
             float ss = 0.f;
             for (int k = 0; k < C; ++k) { float x = fraw[(size_t)k * HW + p]; ss = fmaf(x, x, ss); }
             float den = fmaxf(sqrtf(ss), XQ_EPS);
@@ -878,12 +899,12 @@ ms_decode_kernel(const MsDecArgs a) {
     const bool bsq = d.mode == XQ_MS_BSQ;
     MsSmem s = ms_carve(smem, C, H, W, false);
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < CHW; i += MS_THREADS) s.fhat[i] = 0.f;
+    for (int i = tid; i < CHW; i += blockDim.x) s.fhat[i] = 0.f;
     int64_t off = 0;
     int lpos = 0;
     for (int si = 0; si < d.SN; ++si) {
         const int P = d.patch_nums[si], R = P * P;
-        for (int r = tid; r < R; r += MS_THREADS) s.idx[r] = (int)a.idx_all[off + (int64_t)b * R + r];
+        for (int r = tid; r < R; r += blockDim.x) s.idx[r] = (int)a.idx_all[off + (int64_t)b * R + r];
         if (P != H || P != W) ms_cubic_tables(s, P, H, W);
         __syncthreads();
         ms_gather(s, a.E, C, R, RP, d.V, bsq, d.scaler[si]);
@@ -906,7 +927,7 @@ ms_decode_kernel(const MsDecArgs a) {
             const int Pn = d.patch_nums[si + 1], Rn = Pn * Pn;
             ms_area_pool(s.fhat, s.rows, C, H, W, Pn, RP);
             __syncthreads();
-            for (int i = tid; i < C * Rn; i += MS_THREADS) {
+            for (int i = tid; i < C * Rn; i += blockDim.x) {
                 int rr = i / C, k = i - rr * C;
                 a.var_input[((size_t)b * a.L_var + lpos + rr) * C + k] = s.rows[k * RP + rr];
             }
@@ -915,7 +936,7 @@ ms_decode_kernel(const MsDecArgs a) {
         }
         off += (int64_t)d.B * R;
     }
-    if (a.out) for (int i = tid; i < CHW; i += MS_THREADS) a.out[(size_t)b * CHW + i] = s.fhat[i];
+    if (a.out) for (int i = tid; i < CHW; i += blockDim.x) a.out[(size_t)b * CHW + i] = s.fhat[i];
 }
 
 static int ms_vpad(int V) { return (V + MS_TILE_V - 1) / MS_TILE_V * MS_TILE_V; }
@@ -1103,7 +1124,7 @@ int xq_ms_backward(const xq_ms_desc *d, const float *f, const float *E, const fl
         XQ_CUDA_TRY(cudaMemsetAsync(ws.dbpart, 0, sizeof(float) * (size_t)d->B * d->K * C, stream));
     }
     XQ_CUDA_TRY(cudaFuncSetAttribute(ms_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ms_backward_kernel<<<d->B, MS_THREADS, smem, stream>>>(a);
+    ms_backward_kernel<<<d->B, MS_BWD_THREADS, smem, stream>>>(a);
     XQ_LAUNCH_CHECK("ms_backward_kernel");
     if (d->K > 0) {
         size_t nw = (size_t)d->K * C * C * 9, nb = (size_t)d->K * C;

@@ -109,8 +109,9 @@ residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restr
 // what keeps enough loads in flight to run at HBM speed.  CTA partials -> part[blockIdx][4][D].
 //   g_xout may be null (no later residual gradient), g_y may be null (LN output unused).
 constexpr int NACC = 4;
+constexpr int NACC_S = 2;   // accumulators kept in shared memory (the other two stay in registers)
 template <int NV>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 2)
 residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__restrict__ g_y,
                        const float *__restrict__ x_out, const float *__restrict__ mean_in,
                        const float *__restrict__ rstd_in, const float *__restrict__ ln_w,
@@ -119,10 +120,13 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
                        int M, float *__restrict__ g_x, __nv_bfloat16 *__restrict__ g_branch,
                        float *__restrict__ part) {
     constexpr int D = NV * 128;
-    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC][D]
+    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC_S][D]  (sum G*s*branch, sum G*s)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *acc = acc_s + (size_t)warp * NACC * D;
-    for (int i = lane * 4; i < NACC * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *acc = acc_s + (size_t)warp * NACC_S * D;
+    for (int i = lane * 4; i < NACC_S * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 aw[NV], ab[NV];   // d ln_w, d ln_b partials (registers)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
     __syncwarp();
     for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
         const size_t base = (size_t)row * D;
@@ -138,12 +142,8 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
             if (g_y) {
                 float4 g = load_bf16x4(g_y + base + col);
                 float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
-                float4 a0 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
-                float4 a1 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
-                a0.x += g.x * xh[i].x; a0.y += g.y * xh[i].y; a0.z += g.z * xh[i].z; a0.w += g.w * xh[i].w;
-                a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
-                *reinterpret_cast<float4 *>(acc + 0 * D + col) = a0;
-                *reinterpret_cast<float4 *>(acc + 1 * D + col) = a1;
+                aw[i].x += g.x * xh[i].x; aw[i].y += g.y * xh[i].y; aw[i].z += g.z * xh[i].z; aw[i].w += g.w * xh[i].w;
+                ab[i].x += g.x; ab[i].y += g.y; ab[i].z += g.z; ab[i].w += g.w;
                 gy[i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
                 c1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
                 c2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
@@ -167,23 +167,38 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
             if (branch) {
                 float4 b = load_bf16x4(branch + base + col);
                 float4 gm = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 a2 = *reinterpret_cast<float4 *>(acc + 2 * D + col);
-                float4 a3 = *reinterpret_cast<float4 *>(acc + 3 * D + col);
+                float4 a2 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
+                float4 a3 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
                 float4 Gs = make_float4(G.x * s, G.y * s, G.z * s, G.w * s);
                 a2.x += Gs.x * b.x; a2.y += Gs.y * b.y; a2.z += Gs.z * b.z; a2.w += Gs.w * b.w;
                 a3.x += Gs.x; a3.y += Gs.y; a3.z += Gs.z; a3.w += Gs.w;
-                *reinterpret_cast<float4 *>(acc + 2 * D + col) = a2;
-                *reinterpret_cast<float4 *>(acc + 3 * D + col) = a3;
+                *reinterpret_cast<float4 *>(acc + 0 * D + col) = a2;
+                *reinterpret_cast<float4 *>(acc + 1 * D + col) = a3;
                 if (g_branch) store_bf16x4(g_branch + base + col, make_float4(Gs.x * gm.x, Gs.y * gm.y, Gs.z * gm.z, Gs.w * gm.w));
             }
         }
     }
     __syncthreads();
     float *outp = part + (size_t)blockIdx.x * NACC * D;
-    for (int e = threadIdx.x; e < NACC * D; e += THREADS) {
+    for (int e = threadIdx.x; e < NACC_S * D; e += THREADS) {     // P2, P3 from the shared accumulators
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC * D + e];
+        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC_S * D + e];
+        outp[2 * D + e] = a;
+    }
+    __syncthreads();
+    // P0, P1 from the register accumulators, staged through the (now free) shared buffer warp by warp
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        *reinterpret_cast<float4 *>(acc + 0 * D + col) = aw[i];
+        *reinterpret_cast<float4 *>(acc + 1 * D + col) = ab[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * D; e += THREADS) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC_S * D + e];
         outp[e] = a;
     }
 }
@@ -224,24 +239,38 @@ __device__ __forceinline__ float dgelu_f(float x) {
     return 0.5f * (1.f + erf_as(x * 0.70710678118654752f, e)) + x * 0.3989422804014327f * e;
 }
 
-// y = gelu(x + bias): block = one row slice of NC8 uint4 columns; rows walked with a grid stride.
+// y = gelu(x + bias).  A thread owns column chunk c (8 bf16 = 16 B) and walks rows with a grid stride, RU rows
+// per iteration so that RU independent 16-byte loads are in flight (one load per iteration leaves HBM idle).
+constexpr int GELU_RU = 4;
+__device__ __forceinline__ void load_bias8(const float *bias, int c, float (&bb)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bb[k] = 0.f;
+    if (bias) {
+        float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+}
 __global__ void gelu_fwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, uint4 *__restrict__ y,
                                 int M, int C8) {
-    for (int row = blockIdx.x; row < M; row += gridDim.x) {
-        for (int c = threadIdx.x; c < C8; c += blockDim.x) {
-            uint4 v = x[(size_t)row * C8 + c];
-            __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
-            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (bias) {
-                float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
-                bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-            }
+    for (int c = threadIdx.x; c < C8; c += blockDim.x) {
+        float bb[8];
+        load_bias8(bias, c, bb);
+        for (int row0 = blockIdx.x * GELU_RU; row0 < M; row0 += gridDim.x * GELU_RU) {
+            uint4 v[GELU_RU];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float2 f = __bfloat1622float2(p[k]);
-                p[k] = __floats2bfloat162_rn(gelu_f(f.x + bb[2 * k]), gelu_f(f.y + bb[2 * k + 1]));
+            for (int u = 0; u < GELU_RU; ++u)
+                if (row0 + u < M) v[u] = x[(size_t)(row0 + u) * C8 + c];
+#pragma unroll
+            for (int u = 0; u < GELU_RU; ++u) {
+                if (row0 + u >= M) continue;
+                __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 f = __bfloat1622float2(p[k]);
+                    p[k] = __floats2bfloat162_rn(gelu_f(f.x + bb[2 * k]), gelu_f(f.y + bb[2 * k + 1]));
+                }
+                y[(size_t)(row0 + u) * C8 + c] = v[u];
             }
-            y[(size_t)row * C8 + c] = v;
         }
     }
 }
@@ -251,23 +280,27 @@ __global__ void gelu_fwd_kernel(const uint4 *__restrict__ x, const float *__rest
 __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, const uint4 *__restrict__ gy,
                                 uint4 *__restrict__ gx, float *__restrict__ g_bias, int M, int C8) {
     for (int c = threadIdx.x; c < C8; c += blockDim.x) {
-        float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (bias) {
-            float4 b0 = *reinterpret_cast<const float4 *>(bias + c * 8), b1 = *reinterpret_cast<const float4 *>(bias + c * 8 + 4);
-            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-        }
-        for (int row = blockIdx.x; row < M; row += gridDim.x) {
-            uint4 v = x[(size_t)row * C8 + c], g = gy[(size_t)row * C8 + c];
-            __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v);
-            __nv_bfloat162 *q = reinterpret_cast<__nv_bfloat162 *>(&g);
+        float bb[8], acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        load_bias8(bias, c, bb);
+        for (int row0 = blockIdx.x * GELU_RU; row0 < M; row0 += gridDim.x * GELU_RU) {
+            uint4 v[GELU_RU], g[GELU_RU];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float2 f = __bfloat1622float2(p[k]), h = __bfloat1622float2(q[k]);
-                float r0 = h.x * dgelu_f(f.x + bb[2 * k]), r1 = h.y * dgelu_f(f.y + bb[2 * k + 1]);
-                acc[2 * k] += r0; acc[2 * k + 1] += r1;
-                p[k] = __floats2bfloat162_rn(r0, r1);
+            for (int u = 0; u < GELU_RU; ++u)
+                if (row0 + u < M) { v[u] = x[(size_t)(row0 + u) * C8 + c]; g[u] = gy[(size_t)(row0 + u) * C8 + c]; }
+#pragma unroll
+            for (int u = 0; u < GELU_RU; ++u) {
+                if (row0 + u >= M) continue;
+                __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v[u]);
+                __nv_bfloat162 *q = reinterpret_cast<__nv_bfloat162 *>(&g[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float2 f = __bfloat1622float2(p[k]), h = __bfloat1622float2(q[k]);
+                    float r0 = h.x * dgelu_f(f.x + bb[2 * k]), r1 = h.y * dgelu_f(f.y + bb[2 * k + 1]);
+                    acc[2 * k] += r0; acc[2 * k + 1] += r1;
+                    p[k] = __floats2bfloat162_rn(r0, r1);
+                }
+                gx[(size_t)(row0 + u) * C8 + c] = v[u];
             }
-            gx[(size_t)row * C8 + c] = v;
         }
         if (g_bias) {
 #pragma unroll
@@ -337,7 +370,7 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
     if (workspace_bytes < sizeof(float) * (size_t)grid * NACC * D) return XQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float *part = (float *)workspace;
-    const size_t smem = sizeof(float) * (size_t)WARPS * NACC * D;
+    const size_t smem = sizeof(float) * (size_t)WARPS * NACC_S * D;
     XQV_DISPATCH(D, {
         if (cudaFuncSetAttribute(residual_ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return XQ_ERR_CUDA;
@@ -363,7 +396,7 @@ int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, voi
     if (!x || !y || M <= 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
     int C8 = C / 8;
     int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
-    int grid = M < 148 * 8 ? M : 148 * 8;
+    int grid = (M + GELU_RU - 1) / GELU_RU < 148 * 4 ? (M + GELU_RU - 1) / GELU_RU : 148 * 4;
     gelu_fwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)x, bias, (uint4 *)y, M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
@@ -373,7 +406,7 @@ int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, 
     cudaStream_t st = (cudaStream_t)stream;
     int C8 = C / 8;
     int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
-    int grid = M < 148 * 8 ? M : 148 * 8;
+    int grid = (M + GELU_RU - 1) / GELU_RU < 148 * 4 ? (M + GELU_RU - 1) / GELU_RU : 148 * 4;
     if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
     gelu_bwd_kernel<<<grid, threads, 0, st>>>((const uint4 *)x, bias, (const uint4 *)gy, (uint4 *)gx, g_bias, M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
