@@ -38,7 +38,9 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=6)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "eager"],
+                   help="ours: libxqb200 path; reference: CPU oracle port (the contract's reference arm); eager: the "
+                        "reference's way of computing the path in plain PyTorch on the SAME GPU (extra, informative)")
     p.add_argument("--workload", type=str, default=WORKLOAD)
     p.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -128,7 +130,11 @@ def run_ours(a):
 
     model, margs = build_model(a.workload, dev)
     model.train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    fwd_module = model
+    if a.impl == "eager":
+        from oracle.eager_ref import EagerTokenizer   # baseline leg only: reference-style eager ops, no libxqb200
+        fwd_module = EagerTokenizer(model)
+    net = torch.nn.parallel.DistributedDataParallel(fwd_module, device_ids=[local]) if world > 1 else fwd_module
     opt = torch.optim.AdamW(model.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
     B = a.batch
     g = torch.Generator(device=dev).manual_seed(1234 * world + rank)
@@ -226,7 +232,10 @@ def run_ours(a):
                 "hbm_gbs": gbs, "hbm_frac": gbs / hbm, "tmem_read_floor_ms": tmem_floor_ms,
                 "note": "contraction-bound, not HBM-bound (arithmetic intensity ~1900 FLOP/B, DESIGN.md section 5); "
                         "traffic = dram bytes/launch from the round-1 ncu capture (profiles/)"}
+    if a.impl == "eager":
+        roof = None
     out = {
+        "impl": "ours" if a.impl == "ours" else "eager_gpu",
         "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -239,7 +248,7 @@ def run_ours(a):
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "peak_mem_gib": peak_mem,
         "last_loss": loss_host,
     }
-    if not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline and world == 1 and a.impl == "ours":
         out["cpu_baseline"] = cpu_arm(a, steps=1, warmup=0, state=model.state_dict(), margs=model.config)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -301,6 +310,7 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     if args.impl == "reference":
         run_reference(args)
     else:
