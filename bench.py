@@ -256,8 +256,9 @@ def run_ours(a):
 
 
 # ----------------------------------------------------------------------------------------------
-def cpu_arm(a, steps, warmup, state=None, margs=None):
-    """the oracle port of the same training step on the host cores (bounded sample)."""
+def cpu_arm(a, steps, warmup, state=None, margs=None, budget_s=14.0):
+    """the oracle port of the same training step on the host cores (bounded sample: about `budget_s` seconds of
+    CPU work per timed step, so the whole arm ends within minutes whatever --steps is)."""
     from oracle import vit_ref, xq_oracle as xo
     import torch.nn.functional as F  # noqa: F401
     # measured on the B200 host (128-core Xeon 8562Y+, tools/cpu_probe.py): 16 threads 1.10 img/s, 32 -> 1.05,
@@ -279,7 +280,7 @@ def cpu_arm(a, steps, warmup, state=None, margs=None):
         t0 = time.time()
         ref.train_step(x, opt, dropout=torch.randint(3, SN + 1, (2,)).numpy() if SN > 1 else None)
         per_img = (time.time() - t0) / 2
-        n = int(max(2, min(32, 12.0 / max(per_img, 1e-3))))
+        n = int(max(2, min(32, budget_s / max(per_img, 1e-3))))
     x = torch.rand(n, 3, 256, 256, generator=g) * 2 - 1
     dr = torch.randint(3, SN + 1, (n,)).numpy() if SN > 1 else None
     for _ in range(warmup):
@@ -297,7 +298,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_arm(a, steps=max(1, a.steps), warmup=min(a.warmup, 1))
+    total = max(1, a.steps) + min(a.warmup, 1)
+    base = cpu_arm(a, steps=max(1, a.steps), warmup=min(a.warmup, 1), budget_s=max(2.0, 150.0 / total))
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": base["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

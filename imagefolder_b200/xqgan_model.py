@@ -12,7 +12,7 @@ What differs, all host-side and documented in DESIGN.md:
   * no `print(alpha, beta, delta)` per step (:296);
   * the frozen semantic / detail teachers are built with random weights when no checkpoint is
     available (the reference downloads them, :175,209); `semantic_guide='none'` skips them;
-  * enc_type / dec_type 'cnn' (never selected by a shipped YAML) is not built yet;
+  * enc_type / dec_type 'cnn' (never selected by a shipped YAML) runs on library conv kernels (cnn.py);
   * `img_to_idxBl`, `encode_to_codes`, `decode_tokens` exist (callers in trainer.py:69,122,
     scripts/pretokenization.py:233, demo_util.py:109 expect them; the reference class lacks them).
 """
@@ -28,6 +28,7 @@ import torch.distributed.nn  # noqa: F401  (differentiable all_gather)
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .cnn import Decoder, Encoder
 from .dino_enc import DINOv2Decoder, DINOv2Encoder, create_model
 from .latent_perturbation import add_perturbation
 from .lookup_free_quantize import LFQ
@@ -172,8 +173,8 @@ class VQModel(nn.Module):
                 product_quant=config.product_quant)
             self.quant_conv = nn.Conv2d(self.encoder.embed_dim, config.codebook_embed_dim, 1)
         elif config.enc_type == 'cnn':
-            raise NotImplementedError("enc_type='cnn' (taming-style conv encoder, xqgan_model.py:454) is not built: "
-                                      "every shipped YAML sets enc_type: dinov2 (SURVEY.md 8a, row a13)")
+            self.encoder = Encoder(ch_mult=config.encoder_ch_mult, z_channels=config.z_channels, dropout=config.dropout_p)
+            self.quant_conv = nn.Conv2d(config.z_channels, config.codebook_embed_dim, 1)
         else:
             raise NotImplementedError
 
@@ -186,7 +187,8 @@ class VQModel(nn.Module):
                 abs_pos_embed=config.abs_pos_embed)
             self.post_quant_conv = nn.Conv2d(config.codebook_embed_dim, self.decoder.embed_dim, 1)
         elif config.dec_type == 'cnn':
-            raise NotImplementedError("dec_type='cnn' is not built (see enc_type)")
+            self.decoder = Decoder(ch_mult=config.decoder_ch_mult, z_channels=config.z_channels, dropout=config.dropout_p)
+            self.post_quant_conv = nn.Conv2d(config.codebook_embed_dim, config.z_channels, 1)
         else:
             raise NotImplementedError
 
@@ -211,7 +213,8 @@ class VQModel(nn.Module):
                         using_znorm=config.codebook_l2_norm, scale=config.scale,
                         entropy_weight=config.entropy_loss_ratio, soft_entropy=config.soft_entropy, )
                     for _ in range(self.product_quant)])
-            self.post_quant_conv = nn.Conv2d(config.codebook_embed_dim * self.product_quant, self.decoder.embed_dim, 1)
+            self.post_quant_conv = nn.Conv2d(config.codebook_embed_dim * self.product_quant,
+                                             self.decoder.embed_dim if config.dec_type == 'dinov2' else config.z_channels, 1)
         else:
             if len(config.v_patch_nums) == 1:
                 self.quantize = VectorQuantizer(config.codebook_size, config.codebook_embed_dim,
@@ -249,6 +252,8 @@ class VQModel(nn.Module):
                 self.sem_linear = nn.Conv2d(self.product_quant * config.codebook_embed_dim, config.codebook_embed_dim, 1)
             elif self.half_sem and self.product_quant == 1:
                 self.sem_linear = nn.Conv2d(768, config.codebook_embed_dim // 2, 1)
+            if self.enc_type == 'cnn':
+                self.sem_linear = torch.nn.Linear(384, config.codebook_embed_dim)
             self.sem_loss_weight = config.sem_loss_weight
 
         self.detail_guide = config.detail_guide
@@ -298,13 +303,15 @@ class VQModel(nn.Module):
     def encode(self, x):
         """:241-254 -> continuous latent B x C x (sqrt L) x (sqrt L)  (PQ>1: B x C x (PQ*L) x 1)"""
         h = self.encoder(x)
-        h = self._tokens_to_map(h)
+        if self.enc_type == 'dinov2':
+            h = self._tokens_to_map(h)
         return self.quant_conv(h)
 
     def decode(self, quant, return_quant=False):
         """:256-261"""
         quant = self.post_quant_conv(quant)
-        quant = quant.flatten(2).permute(0, 2, 1)
+        if self.dec_type == 'dinov2':
+            quant = quant.flatten(2).permute(0, 2, 1)
         return self.decoder(quant)
 
     def _split_branches(self, h):
@@ -363,10 +370,14 @@ class VQModel(nn.Module):
             else:
                 z_s = self.semantic_model.forward_features(input)[:, 1:, :]
                 z_s = z_s.reshape(b, 768, 16, 16)
-            z_s = self.quant_conv(z_s).contiguous()
-            semantic_quant = quant_list[-1]
-            z_s = torch.mean(z_s, dim=(2, 3)).contiguous()
-            z_q_ = torch.mean(semantic_quant, dim=(2, 3)).contiguous()
+            if self.enc_type == 'dinov2':
+                z_s = self.quant_conv(z_s).contiguous()
+                semantic_quant = quant_list[-1]
+                z_s = torch.mean(z_s, dim=(2, 3)).contiguous()
+                z_q_ = torch.mean(semantic_quant, dim=(2, 3)).contiguous()
+            else:  # cnn (:318-320)
+                z_q_ = torch.mean(h, dim=(2, 3)).contiguous()
+                z_s = self.sem_linear(z_s.flatten(1)).contiguous()
             n_drop = int(b * self.codebook_drop)
             with torch.autocast(device_type=input.device.type, enabled=False):
                 sem_loss_scale = self.sem_loss_scale
@@ -406,7 +417,8 @@ class VQModel(nn.Module):
         return list(self.quantizes) if self.product_quant > 1 else [self.quantize]
 
     def _latent_branches(self, x):
-        f = self.quant_conv(self._tokens_to_map(self.encoder(x)))
+        h = self.encoder(x)
+        f = self.quant_conv(self._tokens_to_map(h) if self.enc_type == 'dinov2' else h)
         if self.product_quant > 1:
             return self._split_branches(f)
         return [f]
@@ -417,7 +429,8 @@ class VQModel(nn.Module):
         vpn = None if len(self.v_patch_nums) == 1 else self.v_patch_nums
         f_hats_list = [q.f_to_idxBl_or_fhat(f, to_fhat=True, v_patch_nums=vpn) for q, f in zip(self._quantizers(), f_list)]
         f_hats = [self.post_quant_conv(torch.cat(f_hats, dim=1)) for f_hats in zip(*f_hats_list)]
-        f_hats = [f_hat.flatten(2).permute(0, 2, 1) for f_hat in f_hats]
+        if self.dec_type == 'dinov2':
+            f_hats = [f_hat.flatten(2).permute(0, 2, 1) for f_hat in f_hats]
         if last_one:
             return self.decoder(f_hats[-1]).clamp_(-1, 1)
         return [self.decoder(f_hat).clamp_(-1, 1) for f_hat in f_hats]
@@ -453,7 +466,8 @@ class VQModel(nn.Module):
 
     def fhat_to_img(self, f_hat: torch.Tensor):
         f_hat = self.post_quant_conv(f_hat)
-        f_hat = f_hat.flatten(2).permute(0, 2, 1)
+        if self.dec_type == 'dinov2':
+            f_hat = f_hat.flatten(2).permute(0, 2, 1)
         return self.decoder(f_hat).clamp_(-1, 1)
 
     def idxBl_to_var_input(self, gt_idx_Bl):

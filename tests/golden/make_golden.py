@@ -197,7 +197,26 @@ def main():
     case_lfq(LFQ, "msbr_small", 8, 4, MS)
     case_lfq(LFQ, "msbr_14", 14, 3, MS, codebook_drop=0.34)
     case_lfq(LFQ, "lfq_nonorm", 6, 4, [1, 2, 3, 5], using_znorm=False, scale=0.8)
+    case_cnn()
 
+
+def case_cnn(name="cnn_small", seed=5):
+    """reference CNN Encoder / Decoder (xqgan_model.py:454-584), tiny widths, fp32 CPU."""
+    from tokenizer.tokenizer_image.xqgan_model import Decoder, Encoder
+    torch.manual_seed(seed)
+    enc = Encoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    dec = Decoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    x = torch.randn(2, 3, 16, 16)
+    z = torch.randn(2, 8, 8, 8)
+    with torch.no_grad():
+        h, y = enc(x), dec(z)
+    d = dict(x=npy(x), z=npy(z), h=npy(h), y=npy(y))
+    for k, v in enc.state_dict().items():
+        d["enc." + k] = npy(v)
+    for k, v in dec.state_dict().items():
+        d["dec." + k] = npy(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, h.shape, y.shape)
 
 if __name__ == "__main__":
     main()

@@ -98,9 +98,34 @@ def test_model_variants_build():
     assert m.post_quant_conv.in_channels == 24
     m, _ = small_model("RobustTok")
     assert type(m.quantize).__name__ == "VectorQuantizer" and m.quantize.z_channels == 64
-    with pytest.raises(NotImplementedError):
-        VQ_models["VQ-16"]()          # ModelArgs default enc_type='cnn' is not built
+    cnn = VQ_models["VQ-16"](semantic_guide="none", detail_guide="none", v_patch_nums=[16], z_channels=32,
+                             codebook_embed_dim=8, codebook_size=64)     # ModelArgs default enc/dec type 'cnn'
+    keys = set(cnn.state_dict())
+    for k in ["encoder.conv_in.weight", "encoder.conv_blocks.0.res.1.conv2.bias", "encoder.conv_blocks.1.res.0.norm1.weight",
+              "encoder.conv_blocks.2.res.0.nin_shortcut.weight", "encoder.conv_blocks.3.downsample.conv.weight",
+              "encoder.conv_blocks.4.attn.1.proj_out.bias", "encoder.mid.1.q.weight", "encoder.norm_out.weight",
+              "decoder.conv_blocks.0.attn.2.k.weight", "decoder.conv_blocks.3.upsample.conv.bias", "decoder.conv_out.weight"]:
+        assert k in keys, k
+    with torch.no_grad():
+        h = cnn.eval().encode(torch.randn(1, 3, 64, 64))
+        assert h.shape == (1, 8, 4, 4)
+        assert cnn.decode(torch.randn(1, 8, 4, 4)).shape == (1, 3, 64, 64)
+    assert cnn.decoder.last_layer is cnn.decoder.conv_out.weight
     m, _ = small_model("VQ-4096", semantic_guide="dinov2")
     assert not any(p.requires_grad for p in m.semantic_model.parameters())
     m.train()
     assert not m.semantic_model.training
+
+
+def test_cnn_encoder_decoder_match_reference_golden():
+    """row a13: same state_dict -> same outputs as the reference's conv Encoder / Decoder (fp32, CPU)."""
+    from conftest import load_golden
+    from imagefolder_b200.cnn import Decoder, Encoder
+    g = load_golden("cnn_small")
+    enc = Encoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    dec = Decoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    enc.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("enc.")}, strict=True)
+    dec.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("dec.")}, strict=True)
+    with torch.no_grad():
+        np.testing.assert_allclose(enc(torch.tensor(g["x"])).numpy(), g["h"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(dec(torch.tensor(g["z"])).numpy(), g["y"], rtol=1e-4, atol=1e-5)
