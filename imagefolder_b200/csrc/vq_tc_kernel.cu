@@ -29,7 +29,7 @@ namespace xq {
 constexpr int TC_BM = 128;       // rows per CTA  (UMMA M)
 constexpr int TC_BN = 128;       // codes per tile (UMMA N); 2 accumulator stages = 256 TMEM columns -> 2 CTAs / SM
 constexpr int TC_THREADS = 192;
-constexpr int TC_CAP = 24;       // candidate-group slots per row
+constexpr int TC_CAP = 16;       // candidate-group slots per row
 constexpr float TC_EPS = 2.5e-3f;
 constexpr float TC_W = 2.0f * TC_EPS + 2e-6f;
 
@@ -115,23 +115,26 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int rows_per_chunk
     return (uint32_t)(kc * rows_per_chunk * 128 + row * 128 + (((kk >> 2) ^ (row & 7)) << 4) + ((kk & 3) << 2));
 }
 
-// remember a candidate group (score = its maximum, id = group index); compacts the list when it is full
-__device__ __forceinline__ void cand_push(float score, int gid, float *cs, int *cv, int &cnt, int &overflow, float thr) {
+// remember a candidate group: its best score, its runner-up score and the code holding the best score;
+// compacts the list when it is full
+__device__ __forceinline__ void cand_push(float m1, float m2, int code, float *c1, float *c2, int *cv, int &cnt,
+                                          int &overflow, float thr) {
     if (cnt == TC_CAP) {  // drop groups that fell below the threshold since they were stored
         int w = 0;
         for (int e = 0; e < TC_CAP; ++e)
-            if (cs[e] >= thr) { cs[w] = cs[e]; cv[w] = cv[e]; ++w; }
+            if (c1[e] >= thr) { c1[w] = c1[e]; c2[w] = c2[e]; cv[w] = cv[e]; ++w; }
         cnt = w;
     }
-    if (cnt < TC_CAP) { cs[cnt] = score; cv[cnt] = gid; ++cnt; }
+    if (cnt < TC_CAP) { c1[cnt] = m1; c2[cnt] = m2; cv[cnt] = code; ++cnt; }
     else overflow = 1;
 }
 
 struct TcSmem {
     float *A;        // [C/32][128][32]  swizzled
     float *B;        // [NSTAGE][C/32][256][32] swizzled (TMA)
-    float *cand_s;   // [128][CAP]
-    int *cand_v;     // [128][CAP]
+    float *cand_s;   // [128][CAP] best score of the group
+    float *cand_s2;  // [128][CAP] runner-up score of the group
+    int *cand_v;     // [128][CAP] code with the best score (group = code >> 5)
     float *zz, *red;
     int *idx;
     uint64_t *full, *empty, *tfull, *tempty;
@@ -142,7 +145,7 @@ static size_t tc_smem_bytes(int C, int nstage) {
     size_t b = 1024;                                        // alignment slack
     b += (size_t)TC_BM * C * 4;                             // A
     b += (size_t)nstage * TC_BN * C * 4;                    // B
-    b += (size_t)TC_BM * TC_CAP * 8;                        // candidates
+    b += (size_t)TC_BM * TC_CAP * 12;                       // candidates
     b += (size_t)TC_BM * 4 * 2 + 32 * 4;                    // zz, idx, red
     b += 8 * (2 * 8 + 4) + 16;                              // barriers + tmem ptr
     return b;
@@ -164,6 +167,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     s.B = (float *)(base + (size_t)TC_BM * C * 4);
     uint8_t *p = base + (size_t)TC_BM * C * 4 + (size_t)nstage * TC_BN * C * 4;
     s.cand_s = (float *)p; p += (size_t)TC_BM * TC_CAP * 4;
+    s.cand_s2 = (float *)p; p += (size_t)TC_BM * TC_CAP * 4;
     s.cand_v = (int *)p; p += (size_t)TC_BM * TC_CAP * 4;
     s.zz = (float *)p; p += TC_BM * 4;
     s.idx = (int *)p; p += TC_BM * 4;
@@ -267,6 +271,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
         float runmax = -CUDART_INF_F, thr = -CUDART_INF_F;
         int cnt = 0, overflow = 0;
         float *cs = s.cand_s + row * TC_CAP;
+        float *cs2 = s.cand_s2 + row * TC_CAP;
         int *cv = s.cand_v + row * TC_CAP;
         for (int t = 0; t < T; ++t) {
             const int as = t & 1;
@@ -286,9 +291,40 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
                 float m = v[g][0];
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, v[g][j]);
-                if (m >= thr) {          // rare per row (~ln(#groups) times), cheap
-                    if (m > runmax) { runmax = m; thr = runmax - TC_W; }
-                    cand_push(m, (vt >> 5) + g, cs, cv, cnt, overflow, thr);
+                if (m >= thr) {          // rare per row (~ln(#groups) times); branch-free, ILP-friendly body
+                    const int cbase = vt + g * 32;
+                    float m1 = m;
+                    if (cbase + 32 > V) {            // last tile only: padding rows must not take part
+                        m1 = -CUDART_INF_F;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (cbase + j >= V) v[g][j] = -CUDART_INF_F;
+                            m1 = fmaxf(m1, v[g][j]);
+                        }
+                    }
+                    if (m1 >= thr) {
+                        // argmax (first index) by a min-tree over (value == max ? j : 32); and how many codes of the
+                        // group lie within W of the group's own maximum (1 => the group can hold only ONE candidate)
+                        const float lo = m1 - TC_W;
+                        int ia = 32, ib = 32, ic = 32, id = 32;
+                        int na = 0, nb = 0, nc = 0, nd = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            ia = min(ia, v[g][j + 0] == m1 ? j + 0 : 32);
+                            ib = min(ib, v[g][j + 1] == m1 ? j + 1 : 32);
+                            ic = min(ic, v[g][j + 2] == m1 ? j + 2 : 32);
+                            id = min(id, v[g][j + 3] == m1 ? j + 3 : 32);
+                            na += v[g][j + 0] >= lo;
+                            nb += v[g][j + 1] >= lo;
+                            nc += v[g][j + 2] >= lo;
+                            nd += v[g][j + 3] >= lo;
+                        }
+                        const int i1 = min(min(ia, ib), min(ic, id));
+                        const int nW = (na + nb) + (nc + nd);
+                        if (m1 > runmax) { runmax = m1; thr = runmax - TC_W; }
+                        // second slot: m1 again when several codes are within W of it (forces rescoring), else -inf
+                        cand_push(m1, nW > 1 ? m1 : -CUDART_INF_F, cbase + i1, cs, cs2, cv, cnt, overflow, thr);
+                    }
                 }
             }
 
@@ -300,8 +336,17 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
         // contiguous 32*C*4-byte block of En), then a (d, code) lexicographic warp-argmin picks the winner.
         float best_d = CUDART_INF_F;
         int best_v = 0x7fffffff;
+        // A row whose candidate set {codes with approximate score >= final threshold} has exactly ONE element needs
+        // no rescoring: the true argmin provably lies in that set.  (~90 % of rows.)
+        int n_live = 0, multi = 0, uniq = 0;
+        for (int e = 0; e < cnt; ++e)
+            if (cs[e] >= thr) { ++n_live; uniq = cv[e]; multi |= (cs2[e] >= thr); }
+        const bool need = overflow || multi || n_live != 1;
+        if (!need) best_v = uniq;
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
         const unsigned any_overflow = __ballot_sync(0xffffffffu, overflow != 0);
         for (int r = 0; r < 32; ++r) {
+            if (!((need_mask >> r) & 1u)) continue;
             const int rrow = q * 32 + r;
             const int rcnt = __shfl_sync(0xffffffffu, cnt, r);
             const float rthr = __shfl_sync(0xffffffffu, thr, r);
@@ -314,7 +359,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
                 if ((any_overflow >> r) & 1u) gid = e;
                 else {
                     if (s.cand_s[rrow * TC_CAP + e] < rthr) continue;     // warp-uniform
-                    gid = s.cand_v[rrow * TC_CAP + e];
+                    gid = s.cand_v[rrow * TC_CAP + e] >> 5;
                 }
                 const int code = (gid << 5) + lane;
                 float d = CUDART_INF_F;
@@ -344,6 +389,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
             if (lane == r) { best_d = rb_d; best_v = rb_v; }
         }
         s.idx[row] = best_v;
+        if (trace && warp == 2 && lane == 0) dbg[4] = clock64();
     }
     __syncwarp();
     tc_fence_before();
@@ -352,20 +398,19 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN));
     }
-    // ---- common epilogue: gather raw code, renormalise (xqgan_model.py:769-771), STE value, MSE, histogram
+    // ---- common epilogue: z_q = normalised code (xqgan_model.py:769-771).  En[v] (prep kernel) holds exactly
+    // E[v] / max(|E[v]|, eps) computed with the canonical chain, i.e. the bits the exact kernel recomputes here.
     float sq = 0.f;
     if (tid < TC_BM && row0 + tid < N) {
         const int n = row0 + tid;
         int v = s.idx[tid];
         if (v < 0 || v >= V) v = 0;
-        const float *e = E + (size_t)v * C;
-        float ss = 0.f;
-        for (int k = 0; k < C; ++k) { float x = e[k]; ss = fmaf(x, x, ss); }
-        const float den = fmaxf(sqrtf(ss), XQ_EPS);
+        const float *qn = En + (size_t)v * C;
         const int b = n / HW, pp = n - b * HW;
         float *op = out + (size_t)b * C * HW + pp;
+#pragma unroll 4
         for (int k = 0; k < C; ++k) {
-            float qv = e[k] / den;
+            float qv = qn[k];
             float zn = *(const float *)((const uint8_t *)s.A + sw128_off(tid, k, TC_BM));
             float df = qv - zn;
             sq = fmaf(df, df, sq);

@@ -90,3 +90,25 @@ def test_robusttok_perturbation_path():
         dec, (vq, commit, ent, usages), _, _, _ = model(x, 0, 1.0, 0.1, 100)
         (dec.float().pow(2).mean() + vq + commit).backward()
     assert torch.isfinite(model.encoder.latent_tokens.grad).all()
+
+
+@pytest.mark.parametrize("name", ["VQ-8192", "MSVR10P2-4096"])
+def test_pretokenize_round_trip(name, tmp_path):
+    """f-2: image -> tokens -> jsonl -> tokens -> decode_tokens == img_to_reconstructed_img."""
+    from imagefolder_b200 import pretokenize as pt
+    model, _ = small_model(name)
+    model = model.cuda().eval()
+    x = torch.rand(3, 3, 256, 256) * 2 - 1
+    y = torch.tensor([3, 7, 11])
+    path = str(tmp_path / "tokens.jsonl")
+    n = pt.pretokenize(model, [(x, y)], path, flip=True, autocast_dtype=None)
+    assert n == 6
+    recs = list(pt.read_tokens(path))
+    assert [c for c, _ in recs] == [3, 7, 11, 3, 7, 11]
+    toks = torch.stack([t for _, t in recs]).cuda()
+    per_img = 256 if name == "VQ-8192" else 2 * 286
+    assert toks.shape == (6, per_img)
+    with torch.no_grad():
+        rec = model.decode_tokens(pt.unflatten_codes(toks, model))
+        ref = model.img_to_reconstructed_img(torch.cat([x, torch.flip(x, dims=[-1])]).cuda())
+    np.testing.assert_allclose(npy(rec), npy(ref), rtol=1e-5, atol=1e-5)

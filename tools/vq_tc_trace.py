@@ -12,7 +12,7 @@ ops.vq_lookup(z, E, True)
 torch.cuda.synchronize()
 d = dbg.cpu().tolist()
 t0 = d[0]
-print("prologue", d[1] - t0, "epilogue-loop-end", d[2] - t0, "kernel-end", d[3] - t0)
+print("prologue", d[1] - t0, "epilogue-loop-end", d[2] - t0, "rescored", d[4] - t0, "kernel-end", d[3] - t0)
 for t in range(12):
     a = [d[8 + 4 * t + i] - t0 for i in range(4)]
     print(f"tile {t:2d}: mma tempty-ok {a[0]:8d}  full-ok {a[1]:8d}  issued {a[2]:8d} | epi done {a[3]:8d}")
