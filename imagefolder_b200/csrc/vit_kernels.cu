@@ -205,20 +205,37 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
 
 // sums the CTA partials and finishes the four vectors:
 //   d ln_w = P0 ; d ln_b = P1 ; d gamma_ls = P2 + bias * P3 ; d branch_bias = gamma_ls * P3
+// one thread per column, 8 independent loads in flight per accumulator (the serial version was latency-bound)
 __global__ void reduce_parts_kernel(const float *__restrict__ part, int nblocks, int D, const float *__restrict__ ls_gamma,
                                     const float *__restrict__ branch_bias, float *__restrict__ g_ln_w,
                                     float *__restrict__ g_ln_b, float *__restrict__ g_ls_gamma,
                                     float *__restrict__ g_branch_bias) {
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
+    __shared__ float sh[NACC][8][32];
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;       // 8 sub-ranges of the block list per column
+    const int d = blockIdx.x * 32 + lane;
     float p[NACC] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < nblocks; ++b)
+    if (d < D) {
+        for (int b = sub; b < nblocks; b += 8) {
 #pragma unroll
-        for (int q = 0; q < NACC; ++q) p[q] += part[((size_t)b * NACC + q) * D + d];
-    if (g_ln_w) g_ln_w[d] = p[0];
-    if (g_ln_b) g_ln_b[d] = p[1];
-    if (g_ls_gamma) g_ls_gamma[d] = p[2] + (branch_bias ? branch_bias[d] * p[3] : 0.f);
-    if (g_branch_bias) g_branch_bias[d] = (ls_gamma ? ls_gamma[d] : 1.f) * p[3];
+            for (int q = 0; q < NACC; ++q) p[q] += part[((size_t)b * NACC + q) * D + d];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) sh[q][sub][lane] = p[q];
+    __syncthreads();
+    if (sub == 0 && d < D) {
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) a += sh[q][w][lane];
+            p[q] = a;
+        }
+        if (g_ln_w) g_ln_w[d] = p[0];
+        if (g_ln_b) g_ln_b[d] = p[1];
+        if (g_ls_gamma) g_ls_gamma[d] = p[2] + (branch_bias ? branch_bias[d] * p[3] : 0.f);
+        if (g_branch_bias) g_branch_bias[d] = (ls_gamma ? ls_gamma[d] : 1.f) * p[3];
+    }
 }
 
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding);
@@ -379,7 +396,7 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
             ls_gamma, rowscale, rows_per_sample, M, g_x, (__nv_bfloat16 *)g_branch, part);
     });
     if (cudaGetLastError() != cudaSuccess) return XQ_ERR_CUDA;
-    reduce_parts_kernel<<<(D + 127) / 128, 128, 0, st>>>(part, grid, D, ls_gamma, branch_bias, g_ln_w, g_ln_b,
+    reduce_parts_kernel<<<(D + 31) / 32, 256, 0, st>>>(part, grid, D, ls_gamma, branch_bias, g_ln_w, g_ln_b,
                                                         branch ? g_ls_gamma : nullptr, branch ? g_branch_bias : nullptr);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
