@@ -46,8 +46,9 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16 *p, float4 f) {
     *reinterpret_cast<bf16x4 *>(p) = v;
 }
 
-// One warp per row; NV = D / 128 float4 chunks per lane.
+// One warp handles FR = 2 rows (loads of both issued before any arithmetic); NV = D / 128 float4 chunks per lane.
 //   x_new = x + rowscale * gamma_ls * (branch + branch_bias)
+constexpr int FR = 2;
 template <int NV>
 __global__ void __launch_bounds__(THREADS)
 residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ branch,
@@ -57,59 +58,75 @@ residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restr
                        __nv_bfloat16 *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out) {
     constexpr int D = NV * 128;
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const size_t base = (size_t)row * D;
-    float4 v[NV];
-    const float s = (branch && rowscale) ? rowscale[row / rows_per_sample] : 1.f;
+    const int rbase = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * FR;
+    if (rbase >= M) return;
+    float4 v[FR][NV], bv[FR][NV];
+    bool ok[FR];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int col = (i * 32 + lane) * 4;
-        v[i] = *reinterpret_cast<const float4 *>(x + base + col);
+    for (int u = 0; u < FR; ++u) {
+        ok[u] = rbase + u < M;
+        const size_t base = (size_t)(ok[u] ? rbase + u : rbase) * D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            v[u][i] = *reinterpret_cast<const float4 *>(x + base + col);
+            bv[u][i] = branch ? load_bf16x4(branch + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+        if (!ok[u]) continue;
+        const int row = rbase + u;
+        const size_t base = (size_t)row * D;
         if (branch) {
-            float4 b = load_bf16x4(branch + base + col);
-            if (branch_bias) {
-                float4 bb = *reinterpret_cast<const float4 *>(branch_bias + col);
-                b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+            const float s = rowscale ? rowscale[row / rows_per_sample] : 1.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                float4 b = bv[u][i];
+                if (branch_bias) {
+                    float4 bb = *reinterpret_cast<const float4 *>(branch_bias + col);
+                    b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w;
+                }
+                float4 g = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+                v[u][i].x += s * g.x * b.x; v[u][i].y += s * g.y * b.y; v[u][i].z += s * g.z * b.z; v[u][i].w += s * g.w * b.w;
             }
-            float4 g = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-            v[i].x += s * g.x * b.x; v[i].y += s * g.y * b.y; v[i].z += s * g.z * b.z; v[i].w += s * g.w * b.w;
         }
-    }
-    float sum = 0.f;
+        float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mean = warp_sum(sum) * (1.f / D);
-    float sq = 0.f;
+        for (int i = 0; i < NV; ++i) sum += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+        const float mean = warp_sum(sum) * (1.f / D);
+        float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-        sq += a * a + b * b + c * c + d * d;
-    }
-    const float rstd = rsqrtf(warp_sum(sq) * (1.f / D) + eps);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int col = (i * 32 + lane) * 4;
-        if (x_out) *reinterpret_cast<float4 *>(x_out + base + col) = v[i];
-        if (y) {
-            float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
-            float4 b = *reinterpret_cast<const float4 *>(ln_b + col);
-            float4 o;
-            o.x = (v[i].x - mean) * rstd * w.x + b.x; o.y = (v[i].y - mean) * rstd * w.y + b.y;
-            o.z = (v[i].z - mean) * rstd * w.z + b.z; o.w = (v[i].w - mean) * rstd * w.w + b.w;
-            store_bf16x4(y + base + col, o);
+        for (int i = 0; i < NV; ++i) {
+            float a = v[u][i].x - mean, b = v[u][i].y - mean, c = v[u][i].z - mean, d = v[u][i].w - mean;
+            sq += a * a + b * b + c * c + d * d;
         }
+        const float rstd = rsqrtf(warp_sum(sq) * (1.f / D) + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            if (x_out) *reinterpret_cast<float4 *>(x_out + base + col) = v[u][i];
+            if (y) {
+                float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
+                float4 b = *reinterpret_cast<const float4 *>(ln_b + col);
+                float4 o;
+                o.x = (v[u][i].x - mean) * rstd * w.x + b.x; o.y = (v[u][i].y - mean) * rstd * w.y + b.y;
+                o.z = (v[u][i].z - mean) * rstd * w.z + b.z; o.w = (v[u][i].w - mean) * rstd * w.w + b.w;
+                store_bf16x4(y + base + col, o);
+            }
+        }
+        if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
     }
-    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
-// Backward.  Persistent grid; each warp walks rows with a grid stride.  The four column partial sums
-// (d ln_w, d ln_b, sum G*s*branch, sum G*s) live in a per-warp SHARED-MEMORY accumulator (each lane owns
-// its columns, so plain load-add-store, no atomics): registers stay low enough for 3 CTAs / SM, which is
-// what keeps enough loads in flight to run at HBM speed.  CTA partials -> part[blockIdx][4][D].
+// Backward.  Persistent grid; each warp walks rows with a grid stride, RPW = 2 rows per iteration so that twice as
+// many loads are in flight (the kernel is bound by global-load latency: long-scoreboard stalls dominate at 16 warps/SM).
+// The four column partial sums (d ln_w, d ln_b, sum G*s*branch, sum G*s) live in a per-warp SHARED-MEMORY accumulator
+// (each lane owns its columns -> plain load-add-store, no atomics).  CTA partials -> part[blockIdx][4][D].
 //   g_xout may be null (no later residual gradient), g_y may be null (LN output unused).
 constexpr int NACC = 4;
-constexpr int NACC_S = 2;   // accumulators kept in shared memory (the other two stay in registers)
+constexpr int RPW = 2;
 template <int NV>
 __global__ void __launch_bounds__(THREADS, 2)
 residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__restrict__ g_y,
@@ -120,85 +137,107 @@ residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__
                        int M, float *__restrict__ g_x, __nv_bfloat16 *__restrict__ g_branch,
                        float *__restrict__ part) {
     constexpr int D = NV * 128;
-    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC_S][D]  (sum G*s*branch, sum G*s)
+    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *acc = acc_s + (size_t)warp * NACC_S * D;
-    for (int i = lane * 4; i < NACC_S * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 aw[NV], ab[NV];   // d ln_w, d ln_b partials (registers)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    float *acc = acc_s + (size_t)warp * NACC * D;
+    for (int i = lane * 4; i < NACC * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-    for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
-        const size_t base = (size_t)row * D;
-        const float mean = mean_in[row], rstd = rstd_in[row];
-        const float s = (branch && rowscale) ? rowscale[row / rows_per_sample] : 1.f;
-        float4 xh[NV], gy[NV];
-        float c1 = 0.f, c2 = 0.f;
+    const int stride = gridDim.x * WARPS;
+    for (int row0 = blockIdx.x * WARPS + warp; row0 < M; row0 += stride * RPW) {
+        int rows[RPW];
+        bool ok[RPW];
+        float mean[RPW], rstd[RPW], sc[RPW], c1[RPW], c2[RPW];
+        float4 xh[RPW][NV], gy[RPW][NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int col = (i * 32 + lane) * 4;
-            float4 xv = *reinterpret_cast<const float4 *>(x_out + base + col);
-            xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-            if (g_y) {
-                float4 g = load_bf16x4(g_y + base + col);
-                float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
-                aw[i].x += g.x * xh[i].x; aw[i].y += g.y * xh[i].y; aw[i].z += g.z * xh[i].z; aw[i].w += g.w * xh[i].w;
-                ab[i].x += g.x; ab[i].y += g.y; ab[i].z += g.z; ab[i].w += g.w;
-                gy[i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
-                c1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
-                c2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
-            } else {
-                gy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < RPW; ++u) {
+            rows[u] = row0 + u * stride;
+            ok[u] = rows[u] < M;
+            const int r = ok[u] ? rows[u] : row0;
+            mean[u] = mean_in[r];
+            rstd[u] = rstd_in[r];
+            sc[u] = (branch && rowscale) ? rowscale[r / rows_per_sample] : 1.f;
+            c1[u] = c2[u] = 0.f;
+        }
+        // phase 1: issue the loads of both rows back to back, then the per-row statistics
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const size_t base = (size_t)(ok[u] ? rows[u] : row0) * D;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                xh[u][i] = *reinterpret_cast<const float4 *>(x_out + base + col);
+                gy[u][i] = g_y ? load_bf16x4(g_y + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        c1 = warp_sum(c1) * (1.f / D);
-        c2 = warp_sum(c2) * (1.f / D);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int col = (i * 32 + lane) * 4;
-            float4 G;
-            G.x = rstd * (gy[i].x - c1 - xh[i].x * c2); G.y = rstd * (gy[i].y - c1 - xh[i].y * c2);
-            G.z = rstd * (gy[i].z - c1 - xh[i].z * c2); G.w = rstd * (gy[i].w - c1 - xh[i].w * c2);
-            if (g_xout) {
-                float4 r = *reinterpret_cast<const float4 *>(g_xout + base + col);
-                G.x += r.x; G.y += r.y; G.z += r.z; G.w += r.w;
+        for (int u = 0; u < RPW; ++u) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                float4 xv = xh[u][i];
+                xh[u][i] = make_float4((xv.x - mean[u]) * rstd[u], (xv.y - mean[u]) * rstd[u], (xv.z - mean[u]) * rstd[u],
+                                       (xv.w - mean[u]) * rstd[u]);
+                if (g_y && ok[u]) {
+                    float4 g = gy[u][i];
+                    float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
+                    float4 a0 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
+                    float4 a1 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
+                    a0.x += g.x * xh[u][i].x; a0.y += g.y * xh[u][i].y; a0.z += g.z * xh[u][i].z; a0.w += g.w * xh[u][i].w;
+                    a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
+                    *reinterpret_cast<float4 *>(acc + 0 * D + col) = a0;
+                    *reinterpret_cast<float4 *>(acc + 1 * D + col) = a1;
+                    gy[u][i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
+                    c1[u] += gy[u][i].x + gy[u][i].y + gy[u][i].z + gy[u][i].w;
+                    c2[u] += gy[u][i].x * xh[u][i].x + gy[u][i].y * xh[u][i].y + gy[u][i].z * xh[u][i].z + gy[u][i].w * xh[u][i].w;
+                }
             }
-            if (g_x) *reinterpret_cast<float4 *>(g_x + base + col) = G;
-            if (branch) {
-                float4 b = load_bf16x4(branch + base + col);
-                float4 gm = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 a2 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
-                float4 a3 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
-                float4 Gs = make_float4(G.x * s, G.y * s, G.z * s, G.w * s);
-                a2.x += Gs.x * b.x; a2.y += Gs.y * b.y; a2.z += Gs.z * b.z; a2.w += Gs.w * b.w;
-                a3.x += Gs.x; a3.y += Gs.y; a3.z += Gs.z; a3.w += Gs.w;
-                *reinterpret_cast<float4 *>(acc + 0 * D + col) = a2;
-                *reinterpret_cast<float4 *>(acc + 1 * D + col) = a3;
-                if (g_branch) store_bf16x4(g_branch + base + col, make_float4(Gs.x * gm.x, Gs.y * gm.y, Gs.z * gm.z, Gs.w * gm.w));
+        }
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            c1[u] = warp_sum(c1[u]) * (1.f / D);
+            c2[u] = warp_sum(c2[u]) * (1.f / D);
+        }
+        // phase 2
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            if (!ok[u]) continue;
+            const size_t base = (size_t)rows[u] * D;
+            float4 rr[NV], bv[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                rr[i] = g_xout ? *reinterpret_cast<const float4 *>(g_xout + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bv[i] = branch ? load_bf16x4(branch + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                float4 G;
+                G.x = rstd[u] * (gy[u][i].x - c1[u] - xh[u][i].x * c2[u]) + rr[i].x;
+                G.y = rstd[u] * (gy[u][i].y - c1[u] - xh[u][i].y * c2[u]) + rr[i].y;
+                G.z = rstd[u] * (gy[u][i].z - c1[u] - xh[u][i].z * c2[u]) + rr[i].z;
+                G.w = rstd[u] * (gy[u][i].w - c1[u] - xh[u][i].w * c2[u]) + rr[i].w;
+                if (g_x) *reinterpret_cast<float4 *>(g_x + base + col) = G;
+                if (branch) {
+                    float4 gm = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    float4 a2 = *reinterpret_cast<float4 *>(acc + 2 * D + col);
+                    float4 a3 = *reinterpret_cast<float4 *>(acc + 3 * D + col);
+                    float4 Gs = make_float4(G.x * sc[u], G.y * sc[u], G.z * sc[u], G.w * sc[u]);
+                    a2.x += Gs.x * bv[i].x; a2.y += Gs.y * bv[i].y; a2.z += Gs.z * bv[i].z; a2.w += Gs.w * bv[i].w;
+                    a3.x += Gs.x; a3.y += Gs.y; a3.z += Gs.z; a3.w += Gs.w;
+                    *reinterpret_cast<float4 *>(acc + 2 * D + col) = a2;
+                    *reinterpret_cast<float4 *>(acc + 3 * D + col) = a3;
+                    if (g_branch) store_bf16x4(g_branch + base + col, make_float4(Gs.x * gm.x, Gs.y * gm.y, Gs.z * gm.z, Gs.w * gm.w));
+                }
             }
         }
     }
     __syncthreads();
     float *outp = part + (size_t)blockIdx.x * NACC * D;
-    for (int e = threadIdx.x; e < NACC_S * D; e += THREADS) {     // P2, P3 from the shared accumulators
+    for (int e = threadIdx.x; e < NACC * D; e += THREADS) {
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC_S * D + e];
-        outp[2 * D + e] = a;
-    }
-    __syncthreads();
-    // P0, P1 from the register accumulators, staged through the (now free) shared buffer warp by warp
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int col = (i * 32 + lane) * 4;
-        *reinterpret_cast<float4 *>(acc + 0 * D + col) = aw[i];
-        *reinterpret_cast<float4 *>(acc + 1 * D + col) = ab[i];
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 2 * D; e += THREADS) {
-        float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC_S * D + e];
+        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC * D + e];
         outp[e] = a;
     }
 }
@@ -238,22 +277,29 @@ __global__ void reduce_parts_kernel(const float *__restrict__ part, int nblocks,
     }
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding);
-// e = exp(-z^2) is shared with the derivative (z = x / sqrt(2) -> e = exp(-x^2 / 2)).
-__device__ __forceinline__ float erf_as(float z, float e) {
-    float az = fabsf(z);
-    float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
-    float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    float r = fmaf(-poly, e, 1.f);
-    return copysignf(r, z);
+// erf via Abramowitz-Stegun 7.1.28:  erf(a) = 1 - (1 + a1 a + ... + a6 a^6)^-16,  |abs err| <= 3e-7 (far below the bf16
+// output rounding).  ONE special-function op (the reciprocal) per element -- the 7.1.26 form used before needed exp and
+// reciprocal, and the kernel was bound by the 16-lane/clk MUFU pipe, not by HBM.
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float erf_as(float z) {
+    const float a = fabsf(z);
+    float p = fmaf(a, 0.0000430638f, 0.0002765672f);
+    p = fmaf(p, a, 0.0001520143f);
+    p = fmaf(p, a, 0.0092705272f);
+    p = fmaf(p, a, 0.0422820123f);
+    p = fmaf(p, a, 0.0705230784f);
+    p = fmaf(p, a, 1.0f);
+    p = p * p; p = p * p; p = p * p; p = p * p;          // ^16 (overflows to +inf for |z| > ~9 -> erf = 1, as it should)
+    return copysignf(1.0f - rcp_fast(p), z);
 }
 __device__ __forceinline__ float gelu_f(float x) {
-    float e = __expf(-0.5f * x * x);
-    return 0.5f * x * (1.f + erf_as(x * 0.70710678118654752f, e));
+    const float h = 0.5f * x;
+    return fmaf(h, erf_as(x * 0.70710678118654752f), h);
 }
 __device__ __forceinline__ float dgelu_f(float x) {
-    float e = __expf(-0.5f * x * x);
-    return 0.5f * (1.f + erf_as(x * 0.70710678118654752f, e)) + x * 0.3989422804014327f * e;
+    const float e = ex2_fast(x * x * -0.72134752044448170f);      // exp(-x^2 / 2)
+    return fmaf(0.5f, erf_as(x * 0.70710678118654752f), 0.5f) + x * 0.3989422804014327f * e;
 }
 
 // y = gelu(x + bias).  A thread owns column chunk c (8 bf16 = 16 B) and walks rows with a grid stride, RU rows
@@ -369,7 +415,7 @@ int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *bran
     if (!x || M <= 0 || (y && (!ln_w || !ln_b)) || (!x_out && !y)) return XQ_ERR_ARG;
     if (branch && rowscale && rows_per_sample <= 0) return XQ_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    int grid = (M + WARPS - 1) / WARPS;
+    int grid = (M + WARPS * FR - 1) / (WARPS * FR);
     XQV_DISPATCH(D, (residual_ln_fwd_kernel<NV><<<grid, THREADS, 0, st>>>(
                         x, (const __nv_bfloat16 *)branch, branch_bias, ls_gamma, rowscale, rows_per_sample, ln_w, ln_b,
                         eps, M, x_out, (__nv_bfloat16 *)y, mean, rstd)));
@@ -387,7 +433,7 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
     if (workspace_bytes < sizeof(float) * (size_t)grid * NACC * D) return XQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float *part = (float *)workspace;
-    const size_t smem = sizeof(float) * (size_t)WARPS * NACC_S * D;
+    const size_t smem = sizeof(float) * (size_t)WARPS * NACC * D;
     XQV_DISPATCH(D, {
         if (cudaFuncSetAttribute(residual_ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return XQ_ERR_CUDA;
