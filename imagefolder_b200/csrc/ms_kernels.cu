@@ -12,13 +12,16 @@
 //
 // Kernels: ms_forward_kernel, ms_backward_kernel, ms_decode_kernel, ms_finalize_kernel,
 //          bsq_entropy_fwd_kernel, bsq_entropy_bwd_kernel, reduce_batch_kernel, channel_norm_kernel
+#include <cstdlib>
+
 #include "xq_common.cuh"
 
 namespace xq {
 
-constexpr int MS_THREADS = 256;       // forward / decode (the search tiling assumes 16 x 16 threads)
+constexpr int MS_THREADS = 384;       // forward / decode: 12 warps; the search tiling uses the first 256 threads (16 x 16)
 constexpr int MS_BWD_THREADS = 512;   // backward: no search, only latency-bound conv / pooling work -> more warps
 constexpr int MS_TILE_V = 128;
+constexpr int MS_MAX_WARPS = 16;
 
 struct MsArgs {
     xq_ms_desc d;
@@ -38,6 +41,7 @@ struct MsArgs {
     float *partial;       // [B] per-image loss partial
     float *F_last;        // [B,CHW] saved masked f_hat
     float *Fprev01;       // [SN,2,CHW] (BSQ) f_hat before scale si for images 0,1
+    long long *dbg;       // optional clock trace of CTA 0 (dev tool): [4*si + {0: pooled, 1: searched, 2: upsampled, 3: phi}]
 };
 
 // ---- shared-memory carve-up ------------------------------------------------------------
@@ -48,20 +52,24 @@ struct MsSmem {
     int *iy, *ix;                   // bicubic taps
     float *ratio;                   // [SN]
     float *red;                     // [32]
-    float *rbest;                   // [8 warps][16] cross-warp argmin scratch
-    int *ridx;                      // [8][16]
+    float *rbest;                   // [MS_MAX_WARPS][16] cross-warp argmin scratch
+    int *ridx;                      // [MS_MAX_WARPS][16]
+    float *zz;                      // [RP] row norms (L2 metric)
     int *idx;                       // [RP]
     float *w;                       // Phi weights + bias of the current scale [C*C*9 + C]
 };
 // row pitch of the k-major row buffer: padded to the 128-row search block so that tile reads stay in bounds
 __host__ __device__ inline int ms_rp(int H, int W) { return (H * W + 127) / 128 * 128; }
+// the upsampled code map u (input of the 3x3 Phi conv) is stored with a zero border: plane = (H+2) x (W+2)
+__host__ __device__ inline int ms_pw(int W) { return W + 2; }
+__host__ __device__ inline int ms_pp(int H, int W) { return (H + 2) * (W + 2); }
 __host__ __device__ inline size_t ms_fwd_smem_floats(int C, int H, int W, int SN, bool search) {
     size_t chw = (size_t)C * H * W, rp = (size_t)ms_rp(H, W);
-    size_t n = 3 * chw + (size_t)C * rp;
+    size_t n = 2 * chw + (size_t)C * ms_pp(H, W) + 4 + (size_t)C * rp + rp /*zz*/;
     if (search) n += (size_t)2 * C * MS_TILE_V + 2 * MS_TILE_V;
     n += 4 * (size_t)(H + W) * 2;  // wy,wx,iy,ix
-    n += XQ_MAX_SCALES + 32 + 8 * 16 * 2 + rp + 16;
-    n += (size_t)C * C * 9 + C;   // staged Phi weights
+    n += XQ_MAX_SCALES + 32 + MS_MAX_WARPS * 16 * 2 + rp + 16;
+    n += (size_t)C * C * 9 + C + 8;   // staged Phi weights (+ alignment slack)
     return n;
 }
 __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, bool search) {
@@ -70,9 +78,10 @@ __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, boo
     float *p = base;
     s.rest = p; p += chw;
     s.fhat = p; p += chw;
-    s.u = p; p += chw;
+    s.u = p; p += (size_t)C * ms_pp(H, W);
     p = (float *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     s.rows = p; p += (size_t)C * rp;
+    s.zz = p; p += rp;
     if (search) { s.bt = p; p += (size_t)2 * C * MS_TILE_V; s.eet = p; p += 2 * MS_TILE_V; }
     else { s.bt = nullptr; s.eet = nullptr; }
     s.wy = p; p += 4 * H;
@@ -81,9 +90,10 @@ __device__ __forceinline__ MsSmem ms_carve(float *base, int C, int H, int W, boo
     s.ix = (int *)p; p += 4 * W;
     s.ratio = p; p += XQ_MAX_SCALES;
     s.red = p; p += 32;
-    s.rbest = p; p += 8 * 16;
-    s.ridx = (int *)p; p += 8 * 16;
+    s.rbest = p; p += MS_MAX_WARPS * 16;
+    s.ridx = (int *)p; p += MS_MAX_WARPS * 16;
     s.idx = (int *)p; p += rp;
+    p = (float *)(((uintptr_t)p + 15) & ~(uintptr_t)15);    // 16-byte loads of the staged weights
     s.w = p; p += (size_t)C * C * 9 + C;
     return s;
 }
@@ -133,36 +143,64 @@ __device__ __forceinline__ bool better(float k1, int i1, float k2, int i2) {
     return k1 < k2 || (k1 == k2 && i1 < i2);
 }
 
-// Path S: R <= 16 rows; each thread streams codes v = tid, tid+256, ... straight from EnT
-// (coalesced), rows are broadcast from smem.  key = L2 ? (zz+ee)-2dot : -dot ; argmin, first index.
-__device__ void ms_search_small(const MsSmem &s, const float *__restrict__ EnT, const float *__restrict__ ee,
-                                const float *zz_s, int C, int R, int RP, int V, int Vpad, bool l2) {
-    float best[16];
-    int bidx[16];
+// Path S: R <= 16 rows (NROW = R rounded up to 4); every thread streams codes v = tid, tid + blockDim, ... straight
+// from EnT (coalesced, L2-resident), two codes and 8 k-steps of loads in flight; rows are broadcast from smem.
+// key = L2 ? (zz+ee)-2dot : -dot ; argmin, first index.  (GEMV-like: bound by L2 -> SM bandwidth, not FMA.)
+template <int NROW>
+__device__ void ms_search_small_t(const MsSmem &s, const float *__restrict__ EnT, const float *__restrict__ ee,
+                                  const float *zz_s, int C, int R, int RP, int V, int Vpad, bool l2) {
+    float best[NROW];
+    int bidx[NROW];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) { best[r] = CUDART_INF_F; bidx[r] = 0x7fffffff; }
-    for (int v = threadIdx.x; v < V; v += MS_THREADS) {
-        float acc[16];
+    for (int r = 0; r < NROW; ++r) { best[r] = CUDART_INF_F; bidx[r] = 0x7fffffff; }
+    const int step = blockDim.x;
+    for (int v0 = threadIdx.x; v0 < V; v0 += 2 * step) {
+        const int v1 = v0 + step;
+        const bool has1 = v1 < V;
+        float acc0[NROW], acc1[NROW];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-        for (int k = 0; k < C; ++k) {
-            float b = EnT[(size_t)k * Vpad + v];
-            const float4 *a4 = reinterpret_cast<const float4 *>(s.rows + k * RP);
-            float4 a0 = a4[0], a1 = a4[1], a2 = a4[2], a3 = a4[3];
-            float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+        for (int r = 0; r < NROW; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+        for (int k0 = 0; k0 < C; k0 += 8) {
+            float b0[8], b1[8];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r] = fmaf(a[r], b, acc[r]);
+            for (int kk = 0; kk < 8; ++kk) {
+                const bool kin = k0 + kk < C;
+                b0[kk] = kin ? EnT[(size_t)(k0 + kk) * Vpad + v0] : 0.f;
+                b1[kk] = (kin && has1) ? EnT[(size_t)(k0 + kk) * Vpad + v1] : 0.f;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                if (k0 + kk < C) {
+                    const float4 *a4 = reinterpret_cast<const float4 *>(s.rows + (k0 + kk) * RP);
+#pragma unroll
+                    for (int q = 0; q < NROW / 4; ++q) {
+                        const float4 av = a4[q];
+                        acc0[4 * q + 0] = fmaf(av.x, b0[kk], acc0[4 * q + 0]);
+                        acc0[4 * q + 1] = fmaf(av.y, b0[kk], acc0[4 * q + 1]);
+                        acc0[4 * q + 2] = fmaf(av.z, b0[kk], acc0[4 * q + 2]);
+                        acc0[4 * q + 3] = fmaf(av.w, b0[kk], acc0[4 * q + 3]);
+                        acc1[4 * q + 0] = fmaf(av.x, b1[kk], acc1[4 * q + 0]);
+                        acc1[4 * q + 1] = fmaf(av.y, b1[kk], acc1[4 * q + 1]);
+                        acc1[4 * q + 2] = fmaf(av.z, b1[kk], acc1[4 * q + 2]);
+                        acc1[4 * q + 3] = fmaf(av.w, b1[kk], acc1[4 * q + 3]);
+                    }
+                }
+            }
         }
-        float e = l2 ? ee[v] : 0.f;
+        const float e0 = l2 ? ee[v0] : 0.f, e1 = (l2 && has1) ? ee[v1] : 0.f;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            float key = l2 ? fmaf(-2.0f, acc[r], zz_s[r] + e) : -acc[r];
-            if (key < best[r]) { best[r] = key; bidx[r] = v; }
+        for (int r = 0; r < NROW; ++r) {
+            float key = l2 ? fmaf(-2.0f, acc0[r], zz_s[r] + e0) : -acc0[r];
+            if (key < best[r]) { best[r] = key; bidx[r] = v0; }       // v0 < v1: ascending within the thread
+            if (has1) {
+                float key1 = l2 ? fmaf(-2.0f, acc1[r], zz_s[r] + e1) : -acc1[r];
+                if (key1 < best[r]) { best[r] = key1; bidx[r] = v1; }
+            }
         }
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < NROW; ++r) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             float ob = __shfl_xor_sync(0xffffffffu, best[r], o);
@@ -176,17 +214,24 @@ __device__ void ms_search_small(const MsSmem &s, const float *__restrict__ EnT, 
         int r = threadIdx.x;
         float b = s.rbest[r];
         int bi = s.ridx[r];
-        for (int ww = 1; ww < MS_THREADS / 32; ++ww)
+        for (int ww = 1; ww < (int)(blockDim.x >> 5); ++ww)
             if (better(s.rbest[ww * 16 + r], s.ridx[ww * 16 + r], b, bi)) { b = s.rbest[ww * 16 + r]; bi = s.ridx[ww * 16 + r]; }
         s.idx[r] = bi;
     }
     __syncthreads();
 }
+__device__ __forceinline__ void ms_search_small(const MsSmem &s, const float *__restrict__ EnT, const float *__restrict__ ee,
+                                                const float *zz_s, int C, int R, int RP, int V, int Vpad, bool l2) {
+    if (R <= 4) ms_search_small_t<4>(s, EnT, ee, zz_s, C, R, RP, V, Vpad, l2);
+    else if (R <= 8) ms_search_small_t<8>(s, EnT, ee, zz_s, C, R, RP, V, Vpad, l2);
+    else if (R <= 12) ms_search_small_t<12>(s, EnT, ee, zz_s, C, R, RP, V, Vpad, l2);
+    else ms_search_small_t<16>(s, EnT, ee, zz_s, C, R, RP, V, Vpad, l2);
+}
 
 __device__ __forceinline__ void ms_load_tile(const float *__restrict__ EnT, const float *__restrict__ ee, int Vpad,
                                              int C, int v0, float *b_dst, float *ee_dst) {
     int chunks = C * (MS_TILE_V / 4);
-    for (int i = threadIdx.x; i < chunks; i += MS_THREADS) {
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
         int k = i / (MS_TILE_V / 4), c4 = i % (MS_TILE_V / 4);
         cp_async16(b_dst + k * MS_TILE_V + c4 * 4, EnT + (size_t)k * Vpad + v0 + c4 * 4);
     }
@@ -198,7 +243,8 @@ __device__ __forceinline__ void ms_load_tile(const float *__restrict__ EnT, cons
 template <int TR>
 __device__ void ms_search_block(const MsSmem &s, const float *__restrict__ EnT, const float *__restrict__ ee,
                                 const float *zz_s, int C, int r0, int R, int RP, int V, int Vpad, bool l2) {
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 15, ty = (tid >> 4) & 15;
+    const bool active = tid < 256;               // the 16 x 16 compute layout; extra warps only help staging tiles
     float zz[TR], best[TR];
     int bidx[TR];
 #pragma unroll
@@ -228,6 +274,7 @@ __device__ void ms_search_block(const MsSmem &s, const float *__restrict__ EnT, 
         for (int i = 0; i < TR; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        if (active) {
 #pragma unroll 4
         for (int k = 0; k < C; ++k) {
             float a[TR];
@@ -242,13 +289,14 @@ __device__ void ms_search_block(const MsSmem &s, const float *__restrict__ EnT, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        }
         const int vbase = t * MS_TILE_V;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int cj = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
             int v = vbase + cj;
             float e = ee_s[cj];
-            if (v < V) {
+            if (active && v < V) {
 #pragma unroll
                 for (int i = 0; i < TR; ++i) {
                     float key = l2 ? fmaf(-2.0f, acc[i][j], zz[i] + e) : -acc[i][j];
@@ -267,7 +315,7 @@ __device__ void ms_search_block(const MsSmem &s, const float *__restrict__ EnT, 
             if (better(ob, oi, best[i], bidx[i])) { best[i] = ob; bidx[i] = oi; }
         }
         int r = r0 + ty * TR + i;
-        if (tx == 0 && r < R) s.idx[r] = bidx[i];
+        if (active && tx == 0 && r < R) s.idx[r] = bidx[i];
     }
     __syncthreads();
 }
@@ -321,46 +369,60 @@ __device__ __forceinline__ void ms_bicubic_up(const MsSmem &s, int C, int H, int
                 out = fmaf(s.wy[y * 4 + a], inner, out);
             }
         }
-        s.u[i] = out;
+        s.u[(size_t)c * ms_pp(H, W) + (y + 1) * ms_pw(W) + (x + 1)] = out;
     }
 }
 
-// Phi: h = u*(1-r) + (conv3x3(u)+b)*r at (co0..co0+COB-1, y, x).
+// Phi weights + bias of one Phi into shared memory, TRANSPOSED to [ci][tap][co] so that the weights of 4 consecutive
+// output channels are one 16-byte load; bias follows at w_s[C*C*9 ..].
+__device__ __forceinline__ void ms_stage_phi(float *w_s, const float *__restrict__ gw, const float *__restrict__ gb, int C) {
+    for (int i = threadIdx.x; i < C * C * 9; i += blockDim.x) {
+        int co = i % C, cit = i / C;                         // cit = ci * 9 + tap
+        w_s[i] = gw[(size_t)co * C * 9 + cit];
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) w_s[C * C * 9 + i] = gb[i];
+}
+
+// Phi: h = u*(1-r) + (conv3x3(u)+b)*r at (co0..co0+COB-1, y, x).  u is zero-padded (no bounds checks: a padded tap
+// contributes fmaf(w, 0, acc) = acc), w is the staged [ci][tap][co] layout.  Chain order = oracle: bias, then ci, ky, kx.
 template <int COB>
-__device__ __forceinline__ void ms_phi_point(const float *u, const float *__restrict__ w, const float *__restrict__ bias,
-                                             int C, int H, int W, int co0, int y, int x, float r, float h[COB]) {
+__device__ __forceinline__ void ms_phi_point(const float *u, const float *w, const float *bias, int C, int H, int W,
+                                             int co0, int y, int x, float r, float h[COB]) {
+    const int PW = ms_pw(W), PP = ms_pp(H, W);
     float acc[COB];
 #pragma unroll
     for (int j = 0; j < COB; ++j) acc[j] = bias[co0 + j];
+    const float *win = u + y * PW + x;                    // top-left of the 3x3 window in padded coordinates
     for (int ci = 0; ci < C; ++ci) {
-        const float *plane = u + (size_t)ci * H * W;
+        const float *plane = win + (size_t)ci * PP;
+        const float *wc = w + (size_t)ci * 9 * C + co0;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            int yy = y + ky - 1;
-            if (yy < 0 || yy >= H) continue;
+        for (int t = 0; t < 9; ++t) {
+            const float uv = plane[(t / 3) * PW + (t % 3)];
+            float wv[COB];
+            if (COB == 4) {
+                float4 q = *reinterpret_cast<const float4 *>(wc + t * C);
+                wv[0] = q.x; wv[1 % COB] = q.y; wv[2 % COB] = q.z; wv[3 % COB] = q.w;
+            } else {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                int xx = x + kx - 1;
-                if (xx < 0 || xx >= W) continue;
-                float uv = plane[yy * W + xx];
-#pragma unroll
-                for (int j = 0; j < COB; ++j)
-                    acc[j] = fmaf(w[((size_t)(co0 + j) * C + ci) * 9 + ky * 3 + kx], uv, acc[j]);
+                for (int j = 0; j < COB; ++j) wv[j] = wc[t * C + j];
             }
+#pragma unroll
+            for (int j = 0; j < COB; ++j) acc[j] = fmaf(wv[j], uv, acc[j]);
         }
     }
 #pragma unroll
     for (int j = 0; j < COB; ++j) {
-        float uv = u[(size_t)(co0 + j) * H * W + y * W + x];
+        float uv = u[(size_t)(co0 + j) * PP + (y + 1) * PW + (x + 1)];
         h[j] = uv * (1.0f - r) + acc[j] * r;
     }
 }
 
-// visit every (co-group, position): f(co, p, h)
+// visit every (co-group, position): f(co, p, h).  Two positions per thread iteration -> 2*COB independent fma chains.
 template <int COB, typename F>
 __device__ __forceinline__ void ms_phi_foreach(const float *u, const float *w, const float *bias, int C, int H, int W,
                                                float r, F f) {
-    const int HW = H * W, G = C / COB;
+    const int HW = H * W, G = C / COB, PW = ms_pw(W), PP = ms_pp(H, W);
     for (int i = threadIdx.x; i < G * HW; i += blockDim.x) {
         int g = i / HW, p = i - g * HW;
         int y = p / W, x = p - y * W;
@@ -368,7 +430,7 @@ __device__ __forceinline__ void ms_phi_foreach(const float *u, const float *w, c
         if (w) ms_phi_point<COB>(u, w, bias, C, H, W, g * COB, y, x, r, h);
         else {
 #pragma unroll
-            for (int j = 0; j < COB; ++j) h[j] = u[(size_t)(g * COB + j) * HW + p];
+            for (int j = 0; j < COB; ++j) h[j] = u[(size_t)(g * COB + j) * PP + (y + 1) * PW + (x + 1)];
         }
 #pragma unroll
         for (int j = 0; j < COB; ++j) f(g * COB + j, p, h[j]);
@@ -422,13 +484,13 @@ ms_forward_kernel(const MsArgs a) {
 
     for (int i = tid; i < CHW; i += blockDim.x) { s.rest[i] = fb[i]; s.fhat[i] = 0.f; }
     for (int i = tid; i < C * RP; i += blockDim.x) s.rows[i] = 0.f;
+    for (int i = tid; i < C * ms_pp(H, W); i += blockDim.x) s.u[i] = 0.f;     // zero border of the padded planes
     if (a.with_losses) ms_ratios(s, a.nq, d.B, d.SN);
     __syncthreads();
     const float nq_b = (a.with_losses && a.nq) ? a.nq[b] : 3.0e38f;
     float loss_acc = 0.f;  // per-thread partial of sum_si m * sq / ratio
     int64_t off = 0;
-    float *zz_s = s.rbest;  // R<=16 path keeps zz here?  no: rbest is written by the reduction -> use u as scratch
-    zz_s = s.u;             // u is free during the search phase
+    float *zz_s = s.zz;
     int cur_phi = -1;
 
     for (int si = 0; si < d.SN; ++si) {
@@ -436,6 +498,7 @@ ms_forward_kernel(const MsArgs a) {
         ms_area_pool(s.rest, s.rows, C, H, W, P, RP);
         if (P != H || P != W) ms_cubic_tables(s, P, H, W);
         __syncthreads();
+        if (a.dbg && b == 0 && tid == 0) a.dbg[4 * si + 0] = clock64();
         if (bsq) {
             for (int r = tid; r < R; r += blockDim.x) {
                 int code = 0;
@@ -448,6 +511,7 @@ ms_forward_kernel(const MsArgs a) {
             __syncthreads();
             ms_search(s, a, R, RP, zz_s);
         }
+        if (a.dbg && b == 0 && tid == 0) a.dbg[4 * si + 1] = clock64();
         // indices out + histogram
         for (int r = tid; r < R; r += blockDim.x) {
             int v = s.idx[r];
@@ -458,15 +522,14 @@ ms_forward_kernel(const MsArgs a) {
         __syncthreads();
         ms_bicubic_up(s, C, H, W, P, RP);
         __syncthreads();
+        if (a.dbg && b == 0 && tid == 0) a.dbg[4 * si + 2] = clock64();
         if (bsq && a.Fprev01 && b < 2) {
             float *dst = a.Fprev01 + ((size_t)si * 2 + b) * CHW;
             for (int i = tid; i < CHW; i += blockDim.x) dst[i] = s.fhat[i];
         }
         const int kphi = d.K > 0 ? d.phi_map[si] : -1;
         if (kphi >= 0 && kphi != cur_phi) {   // stage this Phi's weights + bias in shared memory
-            const float *gw = a.phi_w + (size_t)kphi * C * C * 9, *gb = a.phi_b + (size_t)kphi * C;
-            for (int i = tid; i < C * C * 9; i += blockDim.x) s.w[i] = gw[i];
-            for (int i = tid; i < C; i += blockDim.x) s.w[C * C * 9 + i] = gb[i];
+            ms_stage_phi(s.w, a.phi_w + (size_t)kphi * C * C * 9, a.phi_b + (size_t)kphi * C, C);
             cur_phi = kphi;
             __syncthreads();
         }
@@ -486,6 +549,7 @@ ms_forward_kernel(const MsArgs a) {
         if (a.with_losses && m) loss_acc += sq / s.ratio[si];
         off += (int64_t)d.B * R;
         __syncthreads();
+        if (a.dbg && b == 0 && tid == 0) a.dbg[4 * si + 3] = clock64();
     }
     // epilogue: out, saved F_last, loss partial
     for (int i = tid; i < CHW; i += blockDim.x) {
@@ -649,17 +713,19 @@ struct MsBwdSmem {
 };
 __host__ __device__ inline size_t ms_bwd_smem_floats(int C, int H, int W) {
     size_t chw = (size_t)C * H * W, rp = (size_t)ms_rp(H, W);
-    return 5 * chw + (size_t)C * rp + chw /*tmp*/ + 8 * (size_t)(H + W) + (size_t)H * H + (size_t)W * W +
-           XQ_MAX_SCALES + rp + 16 + (size_t)C * C * 9 + C;
+    size_t cpp = (size_t)C * ms_pp(H, W);
+    return 3 * chw /*F,S,du*/ + 2 * cpp /*u,dh padded*/ + (size_t)C * rp + chw /*tmp*/ + 8 * (size_t)(H + W) +
+           (size_t)H * H + (size_t)W * W + XQ_MAX_SCALES + rp + 16 + 8 + (size_t)C * C * 9 + C;
 }
 __device__ __forceinline__ MsBwdSmem ms_bwd_carve(float *base, int C, int H, int W) {
     MsBwdSmem s;
     size_t chw = (size_t)C * H * W, rp = (size_t)ms_rp(H, W);
     float *p = base;
+    size_t cpp = (size_t)C * ms_pp(H, W);
     s.F = p; p += chw;
     s.S = p; p += chw;
-    s.u = p; p += chw;
-    s.dh = p; p += chw;
+    s.u = p; p += cpp;      // zero-padded planes
+    s.dh = p; p += cpp;     // zero-padded planes
     s.du = p; p += chw;
     s.tmp = p; p += chw;
     s.rows = p; p += (size_t)C * rp;
@@ -671,6 +737,7 @@ __device__ __forceinline__ MsBwdSmem ms_bwd_carve(float *base, int C, int H, int
     s.Mx = p; p += (size_t)W * W;
     s.ratio = p; p += XQ_MAX_SCALES;
     s.idx = (int *)p; p += rp;
+    p = (float *)(((uintptr_t)p + 15) & ~(uintptr_t)15);    // 16-byte loads of the staged weights
     s.w = p; p += (size_t)C * C * 9 + C;
     return s;
 }
@@ -698,6 +765,8 @@ ms_backward_kernel(const MsBwdArgs a) {
         s.S[i] = 0.f;
         s.tmp[i] = 0.f;
     }
+    const int PW = ms_pw(W), PP = ms_pp(H, W);
+    for (int i = tid; i < C * PP; i += blockDim.x) { s.u[i] = 0.f; s.dh[i] = 0.f; }
     __syncthreads();
     // gf accumulates in global (each element owned by one thread): start from g_out (+ entropy grads)
     float *gfb = a.gf + (size_t)b * CHW;
@@ -737,9 +806,7 @@ ms_backward_kernel(const MsBwdArgs a) {
         __syncthreads();
         const int kphi = d.K > 0 ? d.phi_map[k] : -1;
         if (kphi >= 0 && kphi != cur_phi) {   // stage this Phi's weights + bias in shared memory (4 times per image)
-            const float *gw = a.phi_w + (size_t)kphi * C * C * 9, *gb = a.phi_b + (size_t)kphi * C;
-            for (int i = tid; i < C * C * 9; i += blockDim.x) s.w[i] = gw[i];
-            for (int i = tid; i < C; i += blockDim.x) s.w[C * C * 9 + i] = gb[i];
+            ms_stage_phi(s.w, a.phi_w + (size_t)kphi * C * C * 9, a.phi_b + (size_t)kphi * C, C);
             cur_phi = kphi;
             __syncthreads();
         }
@@ -756,34 +823,42 @@ ms_backward_kernel(const MsBwdArgs a) {
             float S = s.S[e] + c_vq * D;
             s.S[e] = S;
             if (m) gfb[e] += c_cm * D;
-            s.dh[e] = m ? S : 0.f;
+            s.dh[(size_t)co * PP + (p / W + 1) * PW + (p % W + 1)] = m ? S : 0.f;
             s.F[e] = F - (m ? h : 0.f);
         });
         __syncthreads();
         if (!m) continue;  // dh == 0: nothing flows to Phi / codebook at this scale for this image
         // --- Phi backward: du = (1-r) dh + r conv^T(dh) ; dW, db partials
         if (w) {
-            // du
+            // du[ci][y][x] = (1-r) dh[ci][y][x] + r * sum_{co,tap} w[co][ci][tap] dh[co][y-ky+1][x-kx+1]
+            // (padded dh: no bounds checks; staged weights [ci][tap][co]: 4 output channels per 16-byte load)
             for (int i = tid; i < CHW; i += blockDim.x) {
                 int ci = i / HW, p = i - ci * HW;
                 int y = p / W, x = p - y * W;
-                float acc = 0.f;
-                for (int co = 0; co < C; ++co) {
-                    const float *dplane = s.dh + (size_t)co * HW;
-                    const float *wk = w + ((size_t)co * C + ci) * 9;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const float *wc = w + (size_t)ci * 9 * C;
+                const float *dwin = s.dh + (y + 2) * PW + (x + 2);      // dh[.][y+1][x+1] in padded coordinates, + (1,1)
+                if ((C & 3) == 0) {
+                    for (int co = 0; co < C; co += 4) {
+                        const float *d0 = dwin + (size_t)co * PP;
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        int yy = y - ky + 1;
-                        if (yy < 0 || yy >= H) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            int xx = x - kx + 1;
-                            if (xx < 0 || xx >= W) continue;
-                            acc = fmaf(wk[ky * 3 + kx], dplane[yy * W + xx], acc);
+                        for (int t = 0; t < 9; ++t) {
+                            const int off = -(t / 3) * PW - (t % 3);
+                            float4 q = *reinterpret_cast<const float4 *>(wc + t * C + co);
+                            a0 = fmaf(q.x, d0[off], a0);
+                            a1 = fmaf(q.y, d0[PP + off], a1);
+                            a2 = fmaf(q.z, d0[2 * PP + off], a2);
+                            a3 = fmaf(q.w, d0[3 * PP + off], a3);
                         }
                     }
+                } else {
+                    for (int co = 0; co < C; ++co) {
+                        const float *d0 = dwin + (size_t)co * PP;
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) a0 = fmaf(wc[t * C + co], d0[-(t / 3) * PW - (t % 3)], a0);
+                    }
                 }
-                s.du[i] = (1.0f - r) * s.dh[i] + r * acc;
+                s.du[i] = (1.0f - r) * s.dh[(size_t)ci * PP + (y + 1) * PW + (x + 1)] + r * ((a0 + a1) + (a2 + a3));
             }
             // dW[co][ci][tap] += r * sum_p dh[co][p] u[ci][p+shift]  -> per-image partial in global
             if (gv != 0.f) {
@@ -794,34 +869,27 @@ ms_backward_kernel(const MsBwdArgs a) {
                     float acc[9];
 #pragma unroll
                     for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-                    const float *dplane = s.dh + (size_t)co * HW;
-                    const float *uplane = s.u + (size_t)ci * HW;
+                    const float *dplane = s.dh + (size_t)co * PP + PW + 1;   // interior origin
+                    const float *uplane = s.u + (size_t)ci * PP;             // padded origin = interior (-1,-1)
                     for (int y = 0; y < H; ++y)
                         for (int x = 0; x < W; ++x) {
-                            float dv = dplane[y * W + x];
+                            const float dv = dplane[y * PW + x];
+                            const float *uw = uplane + y * PW + x;
 #pragma unroll
-                            for (int ky = 0; ky < 3; ++ky) {
-                                int yy = y + ky - 1;
-                                if (yy < 0 || yy >= H) continue;
-#pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    int xx = x + kx - 1;
-                                    if (xx < 0 || xx >= W) continue;
-                                    acc[ky * 3 + kx] = fmaf(dv, uplane[yy * W + xx], acc[ky * 3 + kx]);
-                                }
-                            }
+                            for (int t = 0; t < 9; ++t) acc[t] = fmaf(dv, uw[(t / 3) * PW + (t % 3)], acc[t]);
                         }
 #pragma unroll
                     for (int t = 0; t < 9; ++t) dW[(size_t)i * 9 + t] += r * acc[t];
                 }
                 for (int co = tid; co < C; co += blockDim.x) {
                     float acc = 0.f;
-                    for (int p = 0; p < HW; ++p) acc += s.dh[(size_t)co * HW + p];
+                    for (int y = 0; y < H; ++y)
+                        for (int x = 0; x < W; ++x) acc += s.dh[(size_t)co * PP + (y + 1) * PW + (x + 1)];
                     db[co] += r * acc;
                 }
             }
         } else {
-            for (int i = tid; i < CHW; i += blockDim.x) s.du[i] = s.dh[i];
+            for (int i = tid; i < CHW; i += blockDim.x) { int c_ = i / HW, p_ = i - c_ * HW; s.du[i] = s.dh[(size_t)c_ * PP + (p_ / W + 1) * PW + (p_ % W + 1)]; }
         }
         __syncthreads();
         // --- bicubic^T and scatter into gE
@@ -900,8 +968,10 @@ ms_decode_kernel(const MsDecArgs a) {
     MsSmem s = ms_carve(smem, C, H, W, false);
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < CHW; i += blockDim.x) s.fhat[i] = 0.f;
+    for (int i = tid; i < C * ms_pp(H, W); i += blockDim.x) s.u[i] = 0.f;
     int64_t off = 0;
     int lpos = 0;
+    int cur_phi = -1;
     for (int si = 0; si < d.SN; ++si) {
         const int P = d.patch_nums[si], R = P * P;
         for (int r = tid; r < R; r += blockDim.x) s.idx[r] = (int)a.idx_all[off + (int64_t)b * R + r];
@@ -912,8 +982,13 @@ ms_decode_kernel(const MsDecArgs a) {
         ms_bicubic_up(s, C, H, W, P, RP);
         __syncthreads();
         const int kphi = d.K > 0 ? d.phi_map[si] : -1;
-        const float *w = kphi >= 0 ? a.phi_w + (size_t)kphi * C * C * 9 : nullptr;
-        const float *bias = kphi >= 0 ? a.phi_b + (size_t)kphi * C : nullptr;
+        if (kphi >= 0 && kphi != cur_phi) {
+            ms_stage_phi(s.w, a.phi_w + (size_t)kphi * C * C * 9, a.phi_b + (size_t)kphi * C, C);
+            cur_phi = kphi;
+            __syncthreads();
+        }
+        const float *w = kphi >= 0 ? s.w : nullptr;
+        const float *bias = kphi >= 0 ? s.w + C * C * 9 : nullptr;
         float *fs = a.fhat_scales ? a.fhat_scales + ((size_t)si * d.B + b) * CHW : nullptr;
         ms_phi_dispatch(s.u, w, bias, C, H, W, d.resi_ratio, [&](int co, int p, float h) {
             int e = co * HW + p;
@@ -1066,6 +1141,8 @@ int xq_ms_forward(const xq_ms_desc *d, const float *f, const float *E, const flo
     a.partial = with_losses ? ws.partial : nullptr;
     a.F_last = saved ? sv.F_last : nullptr;
     a.Fprev01 = (bsq && with_losses) ? sv.Fprev01 : nullptr;
+    a.dbg = nullptr;
+    if (const char *e = getenv("XQ_MS_TRACE")) a.dbg = (long long *)strtoull(e, nullptr, 0);
     XQ_CUDA_TRY(cudaFuncSetAttribute(ms_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ms_forward_kernel<<<d->B, MS_THREADS, smem, stream>>>(a);
     XQ_LAUNCH_CHECK("ms_forward_kernel");
