@@ -94,7 +94,7 @@ def lib() -> ctypes.CDLL:
     L.xq_vit_residual_ln_bwd.argtypes = [f32p, vp, f32p, f32p, f32p, f32p, vp, f32p, f32p, f32p, c_int, c_int, c_int,
                                          f32p, vp, f32p, f32p, f32p, f32p, vp, c_size_t, vp]
     L.xq_vit_pack_qkv.restype = c_int
-    L.xq_vit_pack_qkv.argtypes = [vp, vp, vp, vp, c_size_t, c_int, vp]
+    L.xq_vit_pack_qkv.argtypes = [vp, vp, vp, vp, vp, c_size_t, c_int, vp]
     L.xq_vit_gelu_fwd.restype = c_int
     L.xq_vit_gelu_fwd.argtypes = [vp, f32p, vp, c_int, c_int, vp]
     L.xq_vit_gelu_bwd.restype = c_int

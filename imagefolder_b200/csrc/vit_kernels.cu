@@ -373,17 +373,41 @@ __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__rest
 }
 
 // dq, dk, dv: each [M, C] bf16 dense (what the SDPA backward returns for q/k/v views of a packed
-// [M, 3C] projection) -> dqkv [M, 3C].  One 16-byte vector per thread.
+// [M, 3C] projection) -> dqkv [M, 3C], and (optionally) g_bias [3C] = column sums of dqkv = the gradient of the
+// qkv projection bias, which autograd would otherwise compute with one more full pass over dqkv.
+// A thread owns one 16-byte column chunk of the packed row and walks rows with a grid stride, PACK_RU rows in flight.
+constexpr int PACK_RU = 4;
 __global__ void pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__restrict__ dk, const uint4 *__restrict__ dv,
-                                uint4 *__restrict__ out, size_t M, int C8) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t per_row = (size_t)3 * C8;
-    if (i >= M * per_row) return;
-    size_t row = i / per_row;
-    int c = (int)(i - row * per_row);
-    int which = c / C8, cc = c - which * C8;
-    const uint4 *src = which == 0 ? dq : (which == 1 ? dk : dv);
-    out[i] = src[row * C8 + cc];
+                                uint4 *__restrict__ out, float *__restrict__ g_bias, int M, int C8) {
+    const int per_row = 3 * C8;
+    for (int c = threadIdx.x; c < per_row; c += blockDim.x) {
+        const int which = c / C8, cc = c - which * C8;
+        const uint4 *src = which == 0 ? dq : (which == 1 ? dk : dv);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int row0 = blockIdx.x * PACK_RU; row0 < M; row0 += gridDim.x * PACK_RU) {
+            uint4 v[PACK_RU];
+#pragma unroll
+            for (int u = 0; u < PACK_RU; ++u)
+                if (row0 + u < M) v[u] = src[(size_t)(row0 + u) * C8 + cc];
+#pragma unroll
+            for (int u = 0; u < PACK_RU; ++u) {
+                if (row0 + u >= M) continue;
+                out[(size_t)(row0 + u) * per_row + c] = v[u];
+                if (g_bias) {
+                    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v[u]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float2 f = __bfloat1622float2(p[k]);
+                        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+                    }
+                }
+            }
+        }
+        if (g_bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(g_bias + c * 8 + k, acc[k]);
+        }
+    }
 }
 
 static int bwd_grid() {
@@ -447,11 +471,17 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
-int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, size_t M, int C, void *stream) {
-    if (!dq || !dk || !dv || !dqkv || M == 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
-    size_t n = M * 3 * (size_t)(C / 8);
-    pack_qkv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv, (uint4 *)dqkv, M, C / 8);
+int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, float *g_bias, size_t M, int C,
+                    void *stream) {
+    if (!dq || !dk || !dv || !dqkv || M == 0 || M > 0x7fffffffu || C <= 0 || (C & 7)) return XQ_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C8 = C / 8, per_row = 3 * C8;
+    const int threads = per_row >= 288 ? 288 : (per_row >= 192 ? 192 : 96);
+    const int rows4 = (int)((M + PACK_RU - 1) / PACK_RU);
+    const int grid = rows4 < 148 * 5 ? rows4 : 148 * 5;
+    if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * 3 * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
+    pack_qkv_kernel<<<grid, threads, 0, st>>>((const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv, (uint4 *)dqkv,
+                                              g_bias, (int)M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 

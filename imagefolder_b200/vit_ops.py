@@ -114,6 +114,42 @@ def gelu_bias(x, bias=None):
     return _GeluBias.apply(x, bias)
 
 
+def _sdpa_packed(qkv, num_heads, dropout_p):
+    """q/k/v as strided views of the packed projection (no copies); returns the leaves and the library output."""
+    B, N, C3 = qkv.shape
+    hd = C3 // 3 // num_heads
+    with torch.enable_grad():
+        src = qkv.detach().view(B, N, 3, num_heads, hd)
+        q = src[:, :, 0].transpose(1, 2).requires_grad_(True)
+        k = src[:, :, 1].transpose(1, 2).requires_grad_(True)
+        v = src[:, :, 2].transpose(1, 2).requires_grad_(True)
+        out = F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p)
+    return q, k, v, out
+
+
+def _sdpa_packed_backward(inner, dims, g, want_bias_grad: bool):
+    """d(qkv) [B,N,3C] (+ its column sums = d(bias)) from the SDPA library backward and ONE pack kernel."""
+    q, k, v, out = inner
+    B, N, C = dims
+    H, hd = q.shape[1], q.shape[3]
+    g = g.reshape(B, N, H, hd).transpose(1, 2)
+    dq, dk, dv = torch.autograd.grad(out, (q, k, v), g)
+    dqkv = torch.empty(B, N, 3 * C, dtype=dq.dtype, device=dq.device)
+    flat = [t.transpose(1, 2) for t in (dq, dk, dv)]            # [B,N,H,hd]
+    db = None
+    if all(t.is_contiguous() for t in flat) and dq.dtype == torch.bfloat16:
+        if want_bias_grad:
+            db = torch.empty(3 * C, dtype=torch.float32, device=dq.device)
+        L = _lib()
+        _call("xq_vit_pack_qkv", 1, L.xq_vit_pack_qkv, _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(dqkv),
+              _ptr(db) if db is not None else None, B * N, C, _stream(dq.device))
+    else:  # layout the library did not produce in our runs; keep correctness
+        torch.stack([t.reshape(B, N, C) for t in flat], dim=2, out=dqkv.view(B, N, 3, C))
+        if want_bias_grad:
+            db = dqkv.float().sum((0, 1))
+    return dqkv, db
+
+
 class _PackedAttention(torch.autograd.Function):
     """softmax(q k^T / sqrt(d)) v on the packed projection qkv [B,N,3*H*hd] (vision_transformer.py:175-191).
 
@@ -125,34 +161,14 @@ class _PackedAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, num_heads: int, dropout_p: float):
         B, N, C3 = qkv.shape
-        C = C3 // 3
-        hd = C // num_heads
-        with torch.enable_grad():
-            src = qkv.detach().view(B, N, 3, num_heads, hd)
-            q = src[:, :, 0].transpose(1, 2).requires_grad_(True)
-            k = src[:, :, 1].transpose(1, 2).requires_grad_(True)
-            v = src[:, :, 2].transpose(1, 2).requires_grad_(True)
-            out = F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p)
-        ctx.inner = (q, k, v, out)
-        ctx.dims = (B, N, C)
-        return out.detach().transpose(1, 2).reshape(B, N, C)
+        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
+        ctx.dims = (B, N, C3 // 3)
+        return ctx.inner[3].detach().transpose(1, 2).reshape(B, N, C3 // 3)
 
     @staticmethod
     def backward(ctx, g):
-        q, k, v, out = ctx.inner
-        ctx.inner = None
-        B, N, C = ctx.dims
-        H, hd = q.shape[1], q.shape[3]
-        g = g.reshape(B, N, H, hd).transpose(1, 2)
-        dq, dk, dv = torch.autograd.grad(out, (q, k, v), g)
-        dqkv = torch.empty(B, N, 3 * C, dtype=dq.dtype, device=dq.device)
-        flat = [t.transpose(1, 2) for t in (dq, dk, dv)]            # [B,N,H,hd]
-        if all(t.is_contiguous() for t in flat) and dq.dtype == torch.bfloat16:
-            L = _lib()
-            _call("xq_vit_pack_qkv", 1, L.xq_vit_pack_qkv, _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(dqkv),
-                  B * N, C, _stream(dq.device))
-        else:  # layout the library did not produce in our runs; keep correctness
-            torch.stack([t.reshape(B, N, C) for t in flat], dim=2, out=dqkv.view(B, N, 3, C))
+        inner, ctx.inner = ctx.inner, None
+        dqkv, _ = _sdpa_packed_backward(inner, ctx.dims, g, False)
         return dqkv, None, None
 
 
@@ -160,12 +176,42 @@ def packed_attention(qkv, num_heads, dropout_p=0.0):
     return _PackedAttention.apply(qkv, num_heads, dropout_p)
 
 
+class _QKVAttention(torch.autograd.Function):
+    """qkv = y W^T + b ; attention(qkv)   (vision_transformer.py:175-191) as ONE autograd node, so that the bias
+    gradient is the column sum the pack kernel already has in registers (no separate sum(0) pass over d(qkv)).
+    y [B,N,C] bf16, W [3C,C] / b [3C] fp32 parameters; GEMMs are library calls in bf16 (autocast semantics)."""
+
+    @staticmethod
+    def forward(ctx, y, W, b, num_heads: int, dropout_p: float):
+        B, N, C = y.shape
+        Wb = W.to(torch.bfloat16)
+        qkv = torch.addmm(b.to(torch.bfloat16), y.reshape(B * N, C), Wb.t()).view(B, N, 3 * C)
+        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
+        ctx.dims = (B, N, C)
+        ctx.save_for_backward(y, Wb)
+        return ctx.inner[3].detach().transpose(1, 2).reshape(B, N, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        inner, ctx.inner = ctx.inner, None
+        y, Wb = ctx.saved_tensors
+        B, N, C = ctx.dims
+        dqkv, db = _sdpa_packed_backward(inner, ctx.dims, g, ctx.needs_input_grad[2])
+        d2 = dqkv.view(B * N, 3 * C)
+        dy = (d2 @ Wb).view(B, N, C) if ctx.needs_input_grad[0] else None
+        dW = (d2.t() @ y.reshape(B * N, C)).float() if ctx.needs_input_grad[1] else None
+        return dy, dW, db, None, None
+
+
 def attention_forward(attn, y):
     """Attention.forward (vision_transformer.py:173-197) on the fused path (no qk_norm, no mask)."""
     if not isinstance(attn.q_norm, nn.Identity) or not isinstance(attn.k_norm, nn.Identity):
         return attn(y)
-    qkv = attn.qkv(y)
-    o = packed_attention(qkv, attn.num_heads, attn.attn_drop.p if attn.training else 0.0)
+    p = attn.attn_drop.p if attn.training else 0.0
+    if attn.qkv.bias is not None and y.dtype == torch.bfloat16:
+        o = _QKVAttention.apply(y, attn.qkv.weight, attn.qkv.bias, attn.num_heads, p)
+    else:
+        o = packed_attention(attn.qkv(y), attn.num_heads, p)
     return F.linear(o, attn.proj.weight)      # the proj bias is folded into the next residual_ln
 
 

@@ -195,8 +195,10 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
                            void *g_branch, float *g_ln_w, float *g_ln_b, float *g_ls_gamma, float *g_branch_bias,
                            void *workspace, size_t workspace_bytes, void *stream);
 /*   gradient re-packing of the fused qkv projection (vision_transformer.py:175-176): dq, dk, dv [M,C] bf16
- *   dense -> dqkv [M,3C]; replaces autograd's stack + permute + contiguous copies */
-int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, size_t M, int C, void *stream);
+ *   dense -> dqkv [M,3C]; replaces autograd's stack + permute + contiguous copies.  g_bias [3C] fp32 (may be NULL)
+ *   receives the column sums of dqkv = the gradient of the qkv bias (nn.Linear's backward `sum(0)` pass, fused). */
+int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, float *g_bias, size_t M, int C,
+                    void *stream);
 /*   y = GELU(x + bias) exact-erf form (timm Mlp act_layer=nn.GELU), x / y bf16 [M,C], bias fp32 [C] or NULL,
  *   C % 8 == 0.  Backward also returns g_bias [C] = column sums of gx (may be NULL). */
 int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, void *stream);

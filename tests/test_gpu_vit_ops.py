@@ -142,3 +142,48 @@ def test_packed_attention_matches_explicit_softmax():
     np.testing.assert_allclose(o.float().detach().cpu().numpy(), ref.detach().float().cpu().numpy(), rtol=2e-2, atol=2e-2)
     gr = q2.grad.float().cpu().numpy()
     np.testing.assert_allclose(qkv.grad.float().cpu().numpy(), gr, rtol=3e-2, atol=3e-2 * float(np.abs(gr).max()))
+
+
+def test_qkv_attention_node_matches_linear_plus_attention():
+    """_QKVAttention (projection + attention as one node; bias gradient from the pack kernel's column sums) against
+    nn.Linear + packed_attention with autograd's own sum(0) bias gradient."""
+    from imagefolder_b200.vit_ops import packed_attention, _QKVAttention
+    torch.manual_seed(5)
+    B, N, H, hd = 4, 131, 6, 64
+    C = H * hd
+    y = torch.randn(B, N, C, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    W = (torch.randn(3 * C, C, device="cuda") * C ** -0.5).requires_grad_(True)
+    b = torch.randn(3 * C, device="cuda").requires_grad_(True)
+    g = torch.randn(B, N, C, device="cuda").to(torch.bfloat16)
+    o1 = _QKVAttention.apply(y, W, b, H, 0.0)
+    gy1, gW1, gb1 = torch.autograd.grad(o1, (y, W, b), g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o2 = packed_attention(torch.nn.functional.linear(y, W, b), H)
+    gy2, gW2, gb2 = torch.autograd.grad(o2, (y, W, b), g)
+    assert torch.equal(o1, o2)                                   # same GEMM + same library attention
+    assert gW1.dtype == torch.float32 and gb1.dtype == torch.float32
+    np.testing.assert_allclose(gy1.float().cpu().numpy(), gy2.float().cpu().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(gW1.cpu().numpy(), gW2.cpu().numpy(), rtol=0, atol=0)
+    # the fused bias gradient sums the bf16 d(qkv) in fp32 (autograd: bf16 reduce) -> equal up to bf16 rounding
+    ref = gb2.cpu().numpy()
+    np.testing.assert_allclose(gb1.cpu().numpy(), ref, rtol=1e-2, atol=1e-2 * float(np.abs(ref).max()))
+
+
+def test_pack_qkv_cabi_ragged_rows_and_bias():
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    torch.manual_seed(6)
+    for M, C in [(1, 8), (7, 64), (1031, 768), (4099, 384)]:
+        dq, dk, dv = (torch.randn(M, C, device="cuda").to(torch.bfloat16) for _ in range(3))
+        out = torch.empty(M, 3 * C, device="cuda", dtype=torch.bfloat16)
+        gb = torch.full((3 * C,), 7.0, device="cuda")
+        _capi.check(L.xq_vit_pack_qkv(_capi.ptr(dq), _capi.ptr(dk), _capi.ptr(dv), _capi.ptr(out), _capi.ptr(gb), M, C,
+                                      _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
+        ref = torch.cat([dq, dk, dv], dim=1)
+        assert torch.equal(out, ref)
+        np.testing.assert_allclose(gb.cpu().numpy(), ref.float().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+        out.zero_()
+        _capi.check(L.xq_vit_pack_qkv(_capi.ptr(dq), _capi.ptr(dk), _capi.ptr(dv), _capi.ptr(out), None, M, C,
+                                      _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
+        assert torch.equal(out, ref)
+    assert L.xq_vit_pack_qkv(None, None, None, None, None, 4, 8, None) != 0

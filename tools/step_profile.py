@@ -31,9 +31,24 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
-ev = [e for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA or e.self_device_time_total > 0]
+ev = [e for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: -e.self_device_time_total)
 tot = sum(e.self_device_time_total for e in ev)
 print(f"total device ms {tot/1e3:.1f}")
-for e in ev[:45]:
+for e in ev[:70]:
     print(f"{e.self_device_time_total/1e3:9.2f} ms {100*e.self_device_time_total/tot:5.1f}% n={e.count:5d} {e.key[:110]}")
+
+# GPU idle analysis: gaps between consecutive kernels on the device timeline of the profiled step
+ks = sorted(((e.time_range.start, e.time_range.end) for e in prof.events()
+             if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+if ks:
+    busy_end, idle, gaps = ks[0][1], 0.0, []
+    for st, en in ks[1:]:
+        if st > busy_end:
+            idle += st - busy_end
+            gaps.append(st - busy_end)
+        busy_end = max(busy_end, en)
+    span = busy_end - ks[0][0]
+    gaps.sort(reverse=True)
+    print(f"device span {span/1e3:.1f} ms, idle {idle/1e3:.2f} ms in {len(gaps)} gaps; top gaps us: {[round(g) for g in gaps[:12]]}; "
+          f"median gap us: {gaps[len(gaps)//2] if gaps else 0:.1f}")
