@@ -83,6 +83,8 @@ def lib() -> ctypes.CDLL:
                                  f32p, vp, c_size_t, vp]
     L.xq_ms_decode.restype = c_int
     L.xq_ms_decode.argtypes = [dp, i64p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    L.xq_ms_embed.restype = c_int
+    L.xq_ms_embed.argtypes = [dp, c_int, c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
     L.xq_usage_ema.restype = c_int
     L.xq_usage_ema.argtypes = [f32p, f32p, c_int, c_int, c_int, c_float, f32p, vp]
     L.xq_vit_residual_ln_fwd.restype = c_int
@@ -175,6 +177,6 @@ EXPORTED_SYMBOLS = [
     "xq_strerror", "xq_abi_version", "xq_last_cuda_error", "xq_vq_workspace_bytes", "xq_vq_forward",
     "xq_vq_backward", "xq_perturb_workspace_bytes", "xq_perturb_forward", "xq_perturb_backward",
     "xq_ms_workspace_bytes", "xq_ms_saved_bytes", "xq_ms_total_tokens", "xq_ms_forward", "xq_ms_backward",
-    "xq_ms_decode", "xq_usage_ema", "xq_vit_residual_ln_fwd", "xq_vit_ln_bwd_workspace_bytes",
+    "xq_ms_decode", "xq_ms_embed", "xq_usage_ema", "xq_vit_residual_ln_fwd", "xq_vit_ln_bwd_workspace_bytes",
     "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd", "xq_vit_pack_qkv",
 ]

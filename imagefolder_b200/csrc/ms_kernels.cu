@@ -953,9 +953,13 @@ __global__ void reduce_batch_kernel(const float *__restrict__ part, int B, size_
 // =========================================================================================
 struct MsDecArgs {
     xq_ms_desc d;
-    const int64_t *idx_all;
+    const int64_t *idx_all;   // token form (all SN scales), or null when
+    const float *h_all;       // feature-map form: scales [si0, si1) packed, each [B,C,pn,pn] (embed_to_fhat / AR step)
     const float *E, *phi_w, *phi_b;
+    const float *fhat_in;     // running f_hat to continue from (null = zeros)
     float *out, *fhat_scales, *var_input;
+    float *next;              // [B,C,pn_si1,pn_si1] = area(f_hat) for the following AR step (quant.py:247-258)
+    int si0, si1;
     int L_var;  // sum_{si>=1} pn^2
 };
 
@@ -967,18 +971,28 @@ ms_decode_kernel(const MsDecArgs a) {
     const bool bsq = d.mode == XQ_MS_BSQ;
     MsSmem s = ms_carve(smem, C, H, W, false);
     const int b = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < CHW; i += blockDim.x) s.fhat[i] = 0.f;
+    for (int i = tid; i < CHW; i += blockDim.x) s.fhat[i] = a.fhat_in ? a.fhat_in[(size_t)b * CHW + i] : 0.f;
     for (int i = tid; i < C * ms_pp(H, W); i += blockDim.x) s.u[i] = 0.f;
-    int64_t off = 0;
+    int64_t off = 0;      // token offset (idx form) / element offset (feature-map form)
     int lpos = 0;
     int cur_phi = -1;
-    for (int si = 0; si < d.SN; ++si) {
+    for (int si = a.si0; si < a.si1; ++si) {
         const int P = d.patch_nums[si], R = P * P;
-        for (int r = tid; r < R; r += blockDim.x) s.idx[r] = (int)a.idx_all[off + (int64_t)b * R + r];
+        if (a.h_all) {
+            const float *h = a.h_all + off + (size_t)b * C * R;      // [C][R] of this image
+            for (int i = tid; i < C * R; i += blockDim.x) {
+                int k = i / R, r = i - k * R;
+                s.rows[k * RP + r] = h[i];
+            }
+        } else {
+            for (int r = tid; r < R; r += blockDim.x) s.idx[r] = (int)a.idx_all[off + (int64_t)b * R + r];
+        }
         if (P != H || P != W) ms_cubic_tables(s, P, H, W);
         __syncthreads();
-        ms_gather(s, a.E, C, R, RP, d.V, bsq, d.scaler[si]);
-        __syncthreads();
+        if (!a.h_all) {
+            ms_gather(s, a.E, C, R, RP, d.V, bsq, d.scaler[si]);
+            __syncthreads();
+        }
         ms_bicubic_up(s, C, H, W, P, RP);
         __syncthreads();
         const int kphi = d.K > 0 ? d.phi_map[si] : -1;
@@ -989,7 +1003,7 @@ ms_decode_kernel(const MsDecArgs a) {
         }
         const float *w = kphi >= 0 ? s.w : nullptr;
         const float *bias = kphi >= 0 ? s.w + C * C * 9 : nullptr;
-        float *fs = a.fhat_scales ? a.fhat_scales + ((size_t)si * d.B + b) * CHW : nullptr;
+        float *fs = a.fhat_scales ? a.fhat_scales + ((size_t)(si - a.si0) * d.B + b) * CHW : nullptr;
         ms_phi_dispatch(s.u, w, bias, C, H, W, d.resi_ratio, [&](int co, int p, float h) {
             int e = co * HW + p;
             float F = s.fhat[e] + h;
@@ -1009,9 +1023,18 @@ ms_decode_kernel(const MsDecArgs a) {
             lpos += Rn;
             __syncthreads();
         }
-        off += (int64_t)d.B * R;
+        off += a.h_all ? (int64_t)d.B * C * R : (int64_t)d.B * R;
     }
     if (a.out) for (int i = tid; i < CHW; i += blockDim.x) a.out[(size_t)b * CHW + i] = s.fhat[i];
+    if (a.next && a.si1 < d.SN) {        // feature-map layout [B,C,pn,pn] (what F.interpolate(mode='area') returns)
+        const int Pn = d.patch_nums[a.si1], Rn = Pn * Pn;
+        ms_area_pool(s.fhat, s.rows, C, H, W, Pn, RP);
+        __syncthreads();
+        for (int i = tid; i < C * Rn; i += blockDim.x) {
+            int k = i / Rn, rr = i - k * Rn;
+            a.next[((size_t)b * C + k) * Rn + rr] = s.rows[k * RP + rr];
+        }
+    }
 }
 
 static int ms_vpad(int V) { return (V + MS_TILE_V - 1) / MS_TILE_V * MS_TILE_V; }
@@ -1224,10 +1247,29 @@ int xq_ms_decode(const xq_ms_desc *d, const int64_t *idx_all, const float *E, co
     size_t smem = sizeof(float) * ms_fwd_smem_floats(d->C, d->H, d->W, d->SN, false);
     if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
     MsDecArgs a;
-    a.d = *d; a.idx_all = idx_all; a.E = E; a.phi_w = phi_w; a.phi_b = phi_b;
+    a.d = *d; a.idx_all = idx_all; a.h_all = nullptr; a.E = E; a.phi_w = phi_w; a.phi_b = phi_b;
+    a.fhat_in = nullptr; a.next = nullptr; a.si0 = 0; a.si1 = d->SN;
     a.out = out; a.fhat_scales = fhat_scales; a.var_input = var_input;
     a.L_var = 0;
     for (int si = 1; si < d->SN; ++si) a.L_var += d->patch_nums[si] * d->patch_nums[si];
+    XQ_CUDA_TRY(cudaFuncSetAttribute(ms_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ms_decode_kernel<<<d->B, MS_THREADS, smem, (cudaStream_t)stream_>>>(a);
+    XQ_LAUNCH_CHECK("ms_decode_kernel");
+    return XQ_OK;
+}
+
+int xq_ms_embed(const xq_ms_desc *d, int si0, int si1, const float *h_all, const float *phi_w, const float *phi_b,
+                const float *fhat_in, float *out, float *fhat_scales, float *next, void *stream_) {
+    int rc = ms_check(d);
+    if (rc != XQ_OK) return rc;
+    if (!h_all || si0 < 0 || si1 > d->SN || si0 >= si1) return XQ_ERR_ARG;
+    if (d->K > 0 && (!phi_w || !phi_b)) return XQ_ERR_ARG;
+    size_t smem = sizeof(float) * ms_fwd_smem_floats(d->C, d->H, d->W, d->SN, false);
+    if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
+    MsDecArgs a;
+    a.d = *d; a.idx_all = nullptr; a.h_all = h_all; a.E = nullptr; a.phi_w = phi_w; a.phi_b = phi_b;
+    a.fhat_in = fhat_in; a.next = next; a.si0 = si0; a.si1 = si1;
+    a.out = out; a.fhat_scales = fhat_scales; a.var_input = nullptr; a.L_var = 0;
     XQ_CUDA_TRY(cudaFuncSetAttribute(ms_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ms_decode_kernel<<<d->B, MS_THREADS, smem, (cudaStream_t)stream_>>>(a);
     XQ_LAUNCH_CHECK("ms_decode_kernel");

@@ -142,25 +142,6 @@ class LFQ(_MultiScaleBase):
         out, fs, _ = ops.ms_decode(idx_all, None, w, b, d, want_out=last_one, want_fhat_scales=not last_one)
         return out if last_one else list(fs.unbind(0))
 
-    def embed_to_fhat(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale=True, last_one=False):
-        """:303-343 (feature-map form; library ops)."""
-        ls_f_hat_BChw = []
-        B = ms_h_BChw[0].shape[0]
-        H = W = self.v_patch_nums[-1]
-        SN = len(self.v_patch_nums)
-        f_hat = ms_h_BChw[0].new_zeros(B, self.Cvae, H, W, dtype=torch.float32)
-        for si, pn in enumerate(self.v_patch_nums):
-            h_BChw = ms_h_BChw[si]
-            if si < len(self.v_patch_nums) - 1:
-                h_BChw = F.interpolate(h_BChw, size=(H, W), mode='bicubic')
-            h_BChw = self.quant_resi[si / (SN - 1)](h_BChw)
-            f_hat.add_(h_BChw)
-            if last_one:
-                ls_f_hat_BChw = f_hat
-            else:
-                ls_f_hat_BChw.append(f_hat.clone())
-        return ls_f_hat_BChw
-
     def idxBl_to_var_input(self, gt_ms_idx_Bl: List[torch.Tensor]) -> torch.Tensor:
         """:383-401 (the reference's version reads a non-existent self.embedding; here the BSQ codes
         +-scaler[si] are used, which is what indices_to_bits(idx, si) yields)."""
@@ -177,15 +158,3 @@ class LFQ(_MultiScaleBase):
         idx_all = torch.cat([t.reshape(-1) for t in lists]).to(torch.int64)
         _, _, var = ops.ms_decode(idx_all, None, w, b, d, want_out=False, want_var_input=True)
         return var
-
-    def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor):
-        """:404-415 (library ops)."""
-        HW = self.v_patch_nums[-1]
-        if si != SN - 1:
-            h = self.quant_resi[si / (SN - 1)](F.interpolate(h_BChw, size=(HW, HW), mode='bicubic'))
-            f_hat.add_(h)
-            return f_hat, F.interpolate(f_hat, size=(self.v_patch_nums[si + 1], self.v_patch_nums[si + 1]), mode='area')
-        else:
-            h = self.quant_resi[si / (SN - 1)](h_BChw)
-            f_hat.add_(h)
-            return f_hat, f_hat

@@ -239,6 +239,32 @@ def ms_decode(idx_all, E, phi_w, phi_b, desc, want_out=True, want_fhat_scales=Fa
     return out, fs, var
 
 
+@torch.no_grad()
+def ms_embed(h_all, phi_w, phi_b, desc, si0: int, si1: int, f_hat=None, want_scales=False, want_next=False):
+    """feature-map form of the per-scale step (quant.py:148-166, 247-258): for si in [si0, si1)
+    f_hat += Phi_si(bicubic_up(h_si)).  `f_hat` (fp32 [B,C,H,W], contiguous) is updated IN PLACE when given, as the
+    reference's f_hat.add_ does.  -> (f_hat, per-scale cumulative f_hat [si1-si0,B,C,H,W] | None, next | None)"""
+    dev = h_all.device
+    phi_w = _f32c(phi_w) if phi_w is not None else None
+    phi_b = _f32c(phi_b) if phi_b is not None else None
+    shape = (desc.B, desc.C, desc.H, desc.W)
+    if f_hat is not None:
+        if tuple(f_hat.shape) != shape or f_hat.dtype != torch.float32 or not f_hat.is_contiguous():
+            raise ValueError(f"f_hat must be a contiguous float32 tensor of shape {shape}")
+        out, fin = f_hat, f_hat
+    else:
+        out, fin = torch.empty(shape, dtype=torch.float32, device=dev), None
+    fs = torch.empty((si1 - si0,) + shape, dtype=torch.float32, device=dev) if want_scales else None
+    nxt = None
+    if want_next and si1 < desc.SN:
+        pn = int(desc.patch_nums[si1])
+        nxt = torch.empty(desc.B, desc.C, pn, pn, dtype=torch.float32, device=dev)
+    L = C.lib()
+    C.call("xq_ms_embed", 1, L.xq_ms_embed, desc, int(si0), int(si1), C.ptr(h_all), C.ptr(phi_w), C.ptr(phi_b),
+           C.ptr(fin), C.ptr(out), C.ptr(fs), C.ptr(nxt), C.stream_ptr(dev))
+    return out, fs, nxt
+
+
 def usage_ema_(ema: torch.Tensor, hit: torch.Tensor, record_hit: int, margin: float) -> torch.Tensor:
     """in-place EMA update of all rows + usage percentages (device tensor [rows])."""
     rows = 1 if ema.dim() == 1 else ema.shape[0]

@@ -162,6 +162,59 @@ class _MultiScaleBase(nn.Module):
         return list(usage.unbind(0))
 
 
+    # ===================== feature-map helpers shared by VectorQuantizer2 and LFQ =====================
+    def _embed_steps(self, hs, si0: int, f_hat, want_scales: bool, want_next: bool):
+        """scales [si0, si0+len(hs)) of  f_hat += Phi_si(bicubic_up(h_si))  in ONE fused kernel (xq_ms_embed)."""
+        B = hs[0].shape[0]
+        H = W = self.v_patch_nums[-1]
+        d, w, b, pns = self._desc(B, H, W)
+        d.channel_norm = 0
+        for k, h in enumerate(hs):
+            want = (B, self.Cvae, pns[si0 + k], pns[si0 + k])
+            if tuple(h.shape) != want:
+                raise ValueError(f"scale {si0 + k}: expected a feature map of shape {want}, got {tuple(h.shape)}")
+        h_all = torch.cat([h.detach().to(torch.float32).reshape(-1) for h in hs])
+        return ops.ms_embed(h_all, w, b, d, si0, si0 + len(hs), f_hat, want_scales, want_next)
+
+    def embed_to_fhat(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale=True, last_one=False):
+        """quant.py:148-180 / lookup_free_quantize.py:311-343: per-scale feature maps -> cumulative f_hat(s)."""
+        SN = len(self.v_patch_nums)
+        if all_to_max_scale:
+            if len(ms_h_BChw) != SN:
+                raise ValueError(f"expected {SN} feature maps, got {len(ms_h_BChw)}")
+            out, fs, _ = self._embed_steps(list(ms_h_BChw), 0, None, want_scales=not last_one, want_next=False)
+            return out if last_one else list(fs.unbind(0))
+        # experimental branch of the reference (f_hat grows with the scale; quant.py:167-179) -- library ops
+        ls_f_hat_BChw = []
+        B = ms_h_BChw[0].shape[0]
+        f_hat = ms_h_BChw[0].new_zeros(B, self.Cvae, self.v_patch_nums[0], self.v_patch_nums[0], dtype=torch.float32)
+        for si, pn in enumerate(self.v_patch_nums):
+            f_hat = F.interpolate(f_hat, size=(pn, pn), mode='bicubic')
+            h_BChw = self.quant_resi[si / (SN - 1)](ms_h_BChw[si])
+            f_hat.add_(h_BChw)
+            if last_one:
+                ls_f_hat_BChw = f_hat
+            else:
+                ls_f_hat_BChw.append(f_hat)
+        return ls_f_hat_BChw
+
+    def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor):
+        """quant.py:247-258 / lookup_free_quantize.py:404-415: one VAR inference step; f_hat is updated in place.
+        -> (f_hat, area-pooled f_hat at the next scale)  or  (f_hat, f_hat) at the last scale."""
+        if (SN != len(self.v_patch_nums) or f_hat.dtype != torch.float32 or not f_hat.is_contiguous()
+                or not f_hat.is_cuda):
+            HW = self.v_patch_nums[-1]                     # unusual call: keep the reference's op sequence
+            if si != SN - 1:
+                h = self.quant_resi[si / (SN - 1)](F.interpolate(h_BChw, size=(HW, HW), mode='bicubic'))
+                f_hat.add_(h)
+                pn = self.v_patch_nums[si + 1]
+                return f_hat, F.interpolate(f_hat, size=(pn, pn), mode='area')
+            f_hat.add_(self.quant_resi[si / (SN - 1)](h_BChw))
+            return f_hat, f_hat
+        _, _, nxt = self._embed_steps([h_BChw], si, f_hat, want_scales=False, want_next=si != SN - 1)
+        return f_hat, (nxt if si != SN - 1 else f_hat)
+
+
 class VectorQuantizer2(_MultiScaleBase):
     # VQGAN originally use beta=1.0, never tried 0.25; SD seems using 0.25
     def __init__(
@@ -226,36 +279,6 @@ class VectorQuantizer2(_MultiScaleBase):
         return f_hat, usages, vq, commit, 0
 
     # ===================== inference =====================
-    def embed_to_fhat(self, ms_h_BChw: List[torch.Tensor], all_to_max_scale=True, last_one=False):
-        """quant.py:148-180 (takes per-scale feature maps, not indices) -- library ops."""
-        ls_f_hat_BChw = []
-        B = ms_h_BChw[0].shape[0]
-        H = W = self.v_patch_nums[-1]
-        SN = len(self.v_patch_nums)
-        if all_to_max_scale:
-            f_hat = ms_h_BChw[0].new_zeros(B, self.Cvae, H, W, dtype=torch.float32)
-            for si, pn in enumerate(self.v_patch_nums):
-                h_BChw = ms_h_BChw[si]
-                if si < len(self.v_patch_nums) - 1:
-                    h_BChw = F.interpolate(h_BChw, size=(H, W), mode='bicubic')
-                h_BChw = self.quant_resi[si / (SN - 1)](h_BChw)
-                f_hat.add_(h_BChw)
-                if last_one:
-                    ls_f_hat_BChw = f_hat
-                else:
-                    ls_f_hat_BChw.append(f_hat.clone())
-        else:
-            f_hat = ms_h_BChw[0].new_zeros(B, self.Cvae, self.v_patch_nums[0], self.v_patch_nums[0], dtype=torch.float32)
-            for si, pn in enumerate(self.v_patch_nums):
-                f_hat = F.interpolate(f_hat, size=(pn, pn), mode='bicubic')
-                h_BChw = self.quant_resi[si / (SN - 1)](ms_h_BChw[si])
-                f_hat.add_(h_BChw)
-                if last_one:
-                    ls_f_hat_BChw = f_hat
-                else:
-                    ls_f_hat_BChw.append(f_hat)
-        return ls_f_hat_BChw
-
     def f_to_idxBl_or_fhat(self, f_BChw: torch.Tensor, to_fhat: bool,
                            v_patch_nums: Optional[Sequence[Union[int, Tuple[int, int]]]] = None):
         """quant.py:182-223: list over scales of idx [B, pn*pn] (int64) or cumulative f_hat [B,C,H,W]."""
@@ -292,16 +315,3 @@ class VectorQuantizer2(_MultiScaleBase):
         idx_all = torch.cat([t.reshape(-1) for t in lists]).to(torch.int64)
         _, _, var = ops.ms_decode(idx_all, self.embedding.weight.data, w, b, d, want_out=False, want_var_input=True)
         return var
-
-    # ===================== get_next_autoregressive_input: only used in VAR inference =====================
-    def get_next_autoregressive_input(self, si: int, SN: int, f_hat: torch.Tensor, h_BChw: torch.Tensor):
-        """quant.py:247-258 (per-step feature-map form; library ops)."""
-        HW = self.v_patch_nums[-1]
-        if si != SN - 1:
-            h = self.quant_resi[si / (SN - 1)](F.interpolate(h_BChw, size=(HW, HW), mode='bicubic'))
-            f_hat.add_(h)
-            return f_hat, F.interpolate(f_hat, size=(self.v_patch_nums[si + 1], self.v_patch_nums[si + 1]), mode='area')
-        else:
-            h = self.quant_resi[si / (SN - 1)](h_BChw)
-            f_hat.add_(h)
-            return f_hat, f_hat

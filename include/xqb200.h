@@ -162,6 +162,21 @@ int xq_ms_backward(const xq_ms_desc *d, const float *f, const float *E, const fl
 int xq_ms_decode(const xq_ms_desc *d, const int64_t *idx_all, const float *E, const float *phi_w,
                  const float *phi_b, float *out, float *fhat_scales, float *var_input, void *stream);
 
+/*
+ * The same step in FEATURE-MAP form (the VAR generator's per-step loop and the VAE's embed_to_fhat):
+ *   VectorQuantizer2.embed_to_fhat(all_to_max_scale=True)  quant.py:148-166   -> si0 = 0, si1 = SN, fhat_scales / out
+ *   VectorQuantizer2.get_next_autoregressive_input         quant.py:247-258   -> si1 = si0 + 1, fhat_in = out (in place), next
+ *   (LFQ: lookup_free_quantize.py:311-343, 404-415)
+ * for si in [si0, si1):  f_hat += Phi_si(bicubic_up(h_si))   (no interpolation at the last scale)
+ *   h_all       scales si0..si1-1 packed back to back, each [B,C,pn_si,pn_si] fp32
+ *   fhat_in     [B,C,H,W] running f_hat or NULL (= zeros); may alias out
+ *   out         [B,C,H,W] f_hat after scale si1-1, or NULL
+ *   fhat_scales [si1-si0,B,C,H,W] cumulative f_hat after every scale, or NULL
+ *   next        [B,C,pn_si1,pn_si1] = area-pool of the final f_hat (ignored when si1 == SN), or NULL
+ */
+int xq_ms_embed(const xq_ms_desc *d, int si0, int si1, const float *h_all, const float *phi_w, const float *phi_b,
+                const float *fhat_in, float *out, float *fhat_scales, float *next, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Codebook-usage EMA (xqgan_model.py:777-788, quant.py:121-127,137-141)
  *   ema[rows,V], hit[rows,V]: row i <- copy | 0.9/0.1 | 0.99/0.01 blend of hit[i], chosen by

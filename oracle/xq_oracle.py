@@ -540,6 +540,46 @@ def vq2_f_to_idxBl_or_fhat(f, E, phi_w, phi_b, patch_nums, using_znorm=True, res
     return out
 
 
+def _phi_or_id(u, phi_w, phi_b, k, r):
+    return u if (phi_w is None or k < 0) else phi(u, phi_w[k], phi_b[k], r)
+
+
+def embed_to_fhat(ms_h, phi_w, phi_b, patch_nums, resi_ratio=0.5, last_one=False):
+    """VectorQuantizer2.embed_to_fhat(all_to_max_scale=True) quant.py:148-166 (LFQ: lookup_free_quantize.py:311-328):
+    per-scale feature maps [B,C,pn,pn] -> cumulative f_hat after every scale (or only the last)."""
+    SN = len(patch_nums)
+    H = W = patch_nums[-1]
+    K = 0 if phi_w is None else phi_w.shape[0]
+    pmap = phi_map(SN, K) if K else [-1] * SN
+    B, C = ms_h[0].shape[:2]
+    F = np.zeros((B, C, H, W), np.float32)
+    out = []
+    for si, pn in enumerate(patch_nums):
+        h = _c32(ms_h[si])
+        u = bicubic_up(nchw_to_rows(h), B, C, pn, H, W) if si < SN - 1 else h      # :157-158
+        F = (F + _phi_or_id(u, phi_w, phi_b, pmap[si], resi_ratio)).astype(np.float32)   # :159-160
+        out.append(F.copy())
+    return out[-1] if last_one else out
+
+
+def get_next_autoregressive_input(si, f_hat, h, phi_w, phi_b, patch_nums, resi_ratio=0.5):
+    """VectorQuantizer2.get_next_autoregressive_input quant.py:247-258 (LFQ: lookup_free_quantize.py:404-415).
+    -> (new f_hat, area-pooled f_hat at scale si+1 as [B,C,pn,pn])  /  (f_hat, f_hat) at the last scale."""
+    SN = len(patch_nums)
+    H = W = patch_nums[-1]
+    K = 0 if phi_w is None else phi_w.shape[0]
+    pmap = phi_map(SN, K) if K else [-1] * SN
+    h, f_hat = _c32(h), _c32(f_hat)
+    B, C = h.shape[:2]
+    if si != SN - 1:
+        u = bicubic_up(nchw_to_rows(h), B, C, h.shape[2], H, W)                    # :251-252
+        F = (f_hat + _phi_or_id(u, phi_w, phi_b, pmap[si], resi_ratio)).astype(np.float32)
+        pn = patch_nums[si + 1]
+        return F, rows_to_nchw(area_pool_rows(F, pn), (B, C, pn, pn))             # :254
+    F = (f_hat + _phi_or_id(h, phi_w, phi_b, pmap[si], resi_ratio)).astype(np.float32)   # :256-258
+    return F, F
+
+
 def ema_update(ema_row: np.ndarray, hit: np.ndarray, record_hit: int) -> np.ndarray:
     """quant.py:121-126 / xqgan_model.py:777-782."""
     if record_hit == 0:

@@ -181,8 +181,43 @@ def case_lfq(LFQ, name, C, B, patch_nums, using_znorm=True, codebook_drop=0.5, s
     print(name, "vq", float(vq), "commit", float(commit), "ent", float(ent))
 
 
+def case_var_helpers(Q, name, C, B, patch_nums, seed=11, share=4, **qkw):
+    """feature-map helpers of the VAR side (quant.py:148-180, 247-258; lookup_free_quantize.py:311-343, 404-415):
+    embed_to_fhat(all_to_max_scale=True, last_one=False/True) and the get_next_autoregressive_input chain."""
+    torch.manual_seed(seed)
+    H = patch_nums[-1]
+    SN = len(patch_nums)
+    q = Q(*qkw.pop("args"), v_patch_nums=patch_nums, num_latent_tokens=H * H, share_quant_resi=share, **qkw).eval()
+    phis = list(q.quant_resi.qresi_ls) if share > 1 else [q.quant_resi.qresi]
+    for p in phis:                      # non-trivial Phi weights
+        p.weight.data.normal_(0, 0.2)
+        p.bias.data.normal_(0, 0.1)
+    hs = [torch.randn(B, C, pn, pn) for pn in patch_nums]
+    with torch.no_grad():
+        fh_list = q.embed_to_fhat([h.clone() for h in hs], all_to_max_scale=True, last_one=False)
+        fh_last = q.embed_to_fhat([h.clone() for h in hs], all_to_max_scale=True, last_one=True)
+        f_hat = torch.zeros(B, C, H, H)
+        nexts = []
+        for si in range(SN):
+            f_hat, nxt = q.get_next_autoregressive_input(si, SN, f_hat, hs[si].clone())
+            nexts.append(nxt.clone())
+    d = dict(patch_nums=np.array(patch_nums), phi_w=np.stack([npy(p.weight) for p in phis]),
+             phi_b=np.stack([npy(p.bias) for p in phis]), share=share, fh_last=npy(fh_last), ar_f_hat=npy(f_hat))
+    for si in range(SN):
+        d[f"h{si}"] = npy(hs[si])
+        d[f"fh{si}"] = npy(fh_list[si])
+        d[f"next{si}"] = npy(nexts[si])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "fhat abs max", float(fh_last.abs().max()))
+
+
 def main():
     VQ, VQ2, LFQ, add_perturbation = import_reference()
+    if "--var-helpers-only" in sys.argv:
+        case_var_helpers(VQ2, "varhelp_msvr", 16, 3, [1, 1, 2, 3, 3, 4, 5, 6, 8, 11], args=(256, 16))
+        case_var_helpers(VQ2, "varhelp_shared1", 8, 2, [1, 2, 4, 7], share=1, args=(128, 8), seed=12)
+        case_var_helpers(LFQ, "varhelp_lfq", 10, 2, [1, 2, 3, 5], args=(2 ** 10, 10), seed=13)
+        return
     MS = [1, 1, 2, 3, 3, 4, 5, 6, 8, 11]
     # BASELINE config #1: VQ-4096 (C=64) on one 256x256 image -> 16x16 tokens. Reference init codebook.
     case_vq(VQ, "vq4096_b1", 4096, 64, 1, 16)
@@ -198,6 +233,9 @@ def main():
     case_lfq(LFQ, "msbr_14", 14, 3, MS, codebook_drop=0.34)
     case_lfq(LFQ, "lfq_nonorm", 6, 4, [1, 2, 3, 5], using_znorm=False, scale=0.8)
     case_cnn()
+    case_var_helpers(VQ2, "varhelp_msvr", 16, 3, [1, 1, 2, 3, 3, 4, 5, 6, 8, 11], args=(256, 16))
+    case_var_helpers(VQ2, "varhelp_shared1", 8, 2, [1, 2, 4, 7], share=1, args=(128, 8), seed=12)
+    case_var_helpers(LFQ, "varhelp_lfq", 10, 2, [1, 2, 3, 5], args=(2 ** 10, 10), seed=13)
 
 
 def case_cnn(name="cnn_small", seed=5):

@@ -486,3 +486,90 @@ def test_vq_tcgen05_path_is_bit_identical(B, C, hw, V, init):
     nb = min(B, 4)
     fwd = xo.vq_forward(npy(z[:nb]), npy(E))
     np.testing.assert_array_equal(npy(idx_t[: nb * hw * hw]), fwd["idx"])
+
+
+def _make_varhelp(name):
+    from imagefolder_b200 import VectorQuantizer2, LFQ
+    g = load_golden(name)
+    pn = [int(p) for p in g["patch_nums"]]
+    C = g["h0"].shape[1]
+    share = int(g["share"])
+    if name.endswith("lfq"):
+        q = LFQ(2 ** C, C, v_patch_nums=pn, num_latent_tokens=pn[-1] ** 2, share_quant_resi=share).cuda().eval()
+    else:
+        q = VectorQuantizer2(64, C, v_patch_nums=pn, num_latent_tokens=pn[-1] ** 2, share_quant_resi=share).cuda().eval()
+    for i, m in enumerate(q.quant_resi.modules_list()):
+        m.weight.data.copy_(dev(g["phi_w"][i]))
+        m.bias.data.copy_(dev(g["phi_b"][i]))
+    return q, g, pn
+
+
+@pytest.mark.parametrize("name", ["varhelp_msvr", "varhelp_shared1", "varhelp_lfq"])
+def test_var_feature_map_helpers_golden(name):
+    """row f-3: embed_to_fhat / get_next_autoregressive_input through xq_ms_embed -- bit-exact vs the oracle,
+    within tolerance of the reference modules' own outputs."""
+    q, g, pn = _make_varhelp(name)
+    SN = len(pn)
+    hs = [dev(g[f"h{si}"]) for si in range(SN)]
+    want = xo.embed_to_fhat([g[f"h{si}"] for si in range(SN)], g["phi_w"], g["phi_b"], pn)
+    fl = q.embed_to_fhat(hs, all_to_max_scale=True, last_one=False)
+    assert isinstance(fl, list) and len(fl) == SN
+    for si in range(SN):
+        np.testing.assert_array_equal(npy(fl[si]), want[si])
+        close(fl[si], g[f"fh{si}"])
+    last = q.embed_to_fhat(hs, all_to_max_scale=True, last_one=True)
+    np.testing.assert_array_equal(npy(last), want[-1])
+    close(last, g["fh_last"])
+    # the AR loop of models/var.py:218-229: f_hat is updated in place and returned
+    f_hat = torch.zeros_like(last)
+    Fo = np.zeros_like(want[-1])
+    for si in range(SN):
+        ret, nxt = q.get_next_autoregressive_input(si, SN, f_hat, hs[si])
+        assert ret is f_hat
+        Fo, no = xo.get_next_autoregressive_input(si, Fo, g[f"h{si}"], g["phi_w"], g["phi_b"], pn)
+        np.testing.assert_array_equal(npy(f_hat), Fo)
+        if si != SN - 1:
+            assert tuple(nxt.shape) == g[f"next{si}"].shape
+            np.testing.assert_array_equal(npy(nxt), no)
+            close(nxt, g[f"next{si}"])
+        else:
+            assert nxt is f_hat
+    close(f_hat, g["ar_f_hat"])
+
+
+def test_var_helpers_consistent_with_token_decode_and_errors():
+    """embed_to_fhat on the gathered codes == idx_to_fhat on the tokens (same kernel, two entry forms);
+    wrong shapes raise; unusual calls (SN mismatch) keep the reference op sequence."""
+    from imagefolder_b200 import VectorQuantizer2
+    torch.manual_seed(0)
+    pn = [1, 2, 3, 5, 8]
+    B, C, V = 5, 12, 96
+    q = VectorQuantizer2(V, C, v_patch_nums=pn, num_latent_tokens=64).cuda().eval()
+    q.embedding.weight.data.normal_()
+    idx = [torch.randint(0, V, (B, p * p), device="cuda") for p in pn]
+    hs = [q.embedding(i).transpose(1, 2).reshape(B, C, p, p).contiguous() for i, p in zip(idx, pn)]
+    a = q.embed_to_fhat(hs, last_one=True)
+    b = q.idx_to_fhat(idx)
+    np.testing.assert_array_equal(npy(a), npy(b))
+    var = q.idxBl_to_var_input(idx)                                 # [B, sum_{si>=1} pn^2, C]
+    f_hat = torch.zeros(B, C, 8, 8, device="cuda")
+    pos = 0
+    for si in range(len(pn) - 1):
+        _, nxt = q.get_next_autoregressive_input(si, len(pn), f_hat, hs[si])
+        n = pn[si + 1] ** 2
+        np.testing.assert_array_equal(npy(nxt.reshape(B, C, n).transpose(1, 2)), npy(var[:, pos:pos + n]))
+        pos += n
+    with pytest.raises(ValueError):
+        q.embed_to_fhat(hs[:-1])
+    with pytest.raises(ValueError):
+        q.embed_to_fhat([h[:, :, :1] for h in hs])
+    with pytest.raises(ValueError):
+        q.get_next_autoregressive_input(1, len(pn), f_hat, hs[2])
+    # unusual call (non-contiguous f_hat view): the reference's op sequence on library kernels, same values
+    fv = torch.zeros(B, C, 8, 16, device="cuda")[:, :, :, ::2]
+    f32 = torch.zeros(B, C, 8, 8, device="cuda")
+    rv, nv = q.get_next_autoregressive_input(0, len(pn), fv, hs[0])
+    r32, n32 = q.get_next_autoregressive_input(0, len(pn), f32, hs[0])
+    assert rv is fv
+    close(r32, npy(rv))
+    close(n32, npy(nv))

@@ -116,3 +116,24 @@ def test_lfq(name):
     close(gf, g["gf"])
     close(gw, g["gphi_w"])
     close(gb, g["gphi_b"])
+
+
+@pytest.mark.parametrize("name", ["varhelp_msvr", "varhelp_shared1", "varhelp_lfq"])
+def test_var_feature_map_helpers(name):
+    """oracle embed_to_fhat / get_next_autoregressive_input vs the reference modules' outputs
+    (quant.py:148-166, 247-258; lookup_free_quantize.py:311-328, 404-415)."""
+    g = load_golden(name)
+    pn = [int(p) for p in g["patch_nums"]]
+    SN = len(pn)
+    hs = [g[f"h{si}"] for si in range(SN)]
+    fl = xo.embed_to_fhat(hs, g["phi_w"], g["phi_b"], pn)
+    for si in range(SN):
+        close(fl[si], g[f"fh{si}"])
+    close(xo.embed_to_fhat(hs, g["phi_w"], g["phi_b"], pn, last_one=True), g["fh_last"])
+    F = np.zeros_like(g["fh_last"])
+    for si in range(SN):
+        F, nxt = xo.get_next_autoregressive_input(si, F, hs[si], g["phi_w"], g["phi_b"], pn)
+        assert nxt.shape == g[f"next{si}"].shape
+        close(nxt, g[f"next{si}"])
+    close(F, g["ar_f_hat"])
+    np.testing.assert_array_equal(F, fl[-1])          # the AR chain and embed_to_fhat are the same arithmetic
