@@ -97,6 +97,8 @@ def lib() -> ctypes.CDLL:
                                          f32p, vp, f32p, f32p, f32p, f32p, vp, c_size_t, vp]
     L.xq_vit_pack_qkv.restype = c_int
     L.xq_vit_pack_qkv.argtypes = [vp, vp, vp, vp, vp, c_size_t, c_int, vp]
+    L.xq_vit_patchify.restype = c_int
+    L.xq_vit_patchify.argtypes = [f32p, vp, c_int, c_int, c_int, c_int, c_int, vp]
     L.xq_vit_gelu_fwd.restype = c_int
     L.xq_vit_gelu_fwd.argtypes = [vp, f32p, vp, c_int, c_int, vp]
     L.xq_vit_gelu_bwd.restype = c_int
@@ -106,13 +108,14 @@ def lib() -> ctypes.CDLL:
 
 
 # --- instrumentation used by bench.py (off by default) ---------------------------------------
-TIMING = None        # dict name -> [(start_event, end_event), ...] when enabled
+TIMING = None        # dict name -> [(start_event, end_event, algorithmic_bytes), ...] when enabled
 LAUNCHES = [0]       # number of libxqb200 kernels launched (counted per C call)
 
 
-def call(name: str, n_kernels: int, fn, *args) -> None:
+def call(name: str, n_kernels: int, fn, *args, nbytes: int = 0) -> None:
     """invoke a C-ABI entry point, map its return code, count its kernel launches and (when
-    TIMING is enabled) bracket it with CUDA events on the current stream."""
+    TIMING is enabled) bracket it with CUDA events on the current stream.  `nbytes` = the call's algorithmic
+    HBM bytes (what it must read + write once), recorded for bench.py's per-kernel roofline table."""
     LAUNCHES[0] += n_kernels
     if TIMING is None:
         check(fn(*args), name)
@@ -121,7 +124,7 @@ def call(name: str, n_kernels: int, fn, *args) -> None:
     s.record()
     rc = fn(*args)
     e.record()
-    TIMING.setdefault(name, []).append((s, e))
+    TIMING.setdefault(name, []).append((s, e, nbytes))
     check(rc, name)
 
 
@@ -178,5 +181,5 @@ EXPORTED_SYMBOLS = [
     "xq_vq_backward", "xq_perturb_workspace_bytes", "xq_perturb_forward", "xq_perturb_backward",
     "xq_ms_workspace_bytes", "xq_ms_saved_bytes", "xq_ms_total_tokens", "xq_ms_forward", "xq_ms_backward",
     "xq_ms_decode", "xq_ms_embed", "xq_usage_ema", "xq_vit_residual_ln_fwd", "xq_vit_ln_bwd_workspace_bytes",
-    "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd", "xq_vit_pack_qkv",
+    "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd", "xq_vit_pack_qkv", "xq_vit_patchify",
 ]

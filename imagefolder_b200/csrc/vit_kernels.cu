@@ -315,43 +315,54 @@ __device__ __forceinline__ void load_bias8(const float *bias, int c, float (&bb)
 }
 __global__ void gelu_fwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, uint4 *__restrict__ y,
                                 int M, int C8) {
+    // NON-persistent: one CTA per GELU_RU rows.  tools/mb/stream_mb.cu on B200: fresh small CTAs stream at 6.1 TB/s where
+    // the persistent grid-stride form of the same loop reaches 5.4 (lock-step load/store phases + SM imbalance).
+    const int row0 = blockIdx.x * GELU_RU;
     for (int c = threadIdx.x; c < C8; c += blockDim.x) {
         float bb[8];
         load_bias8(bias, c, bb);
-        for (int row0 = blockIdx.x * GELU_RU; row0 < M; row0 += gridDim.x * GELU_RU) {
-            uint4 v[GELU_RU];
+        uint4 v[GELU_RU];
 #pragma unroll
-            for (int u = 0; u < GELU_RU; ++u)
-                if (row0 + u < M) v[u] = x[(size_t)(row0 + u) * C8 + c];
+        for (int u = 0; u < GELU_RU; ++u)
+            if (row0 + u < M) v[u] = x[(size_t)(row0 + u) * C8 + c];
 #pragma unroll
-            for (int u = 0; u < GELU_RU; ++u) {
-                if (row0 + u >= M) continue;
-                __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v[u]);
+        for (int u = 0; u < GELU_RU; ++u) {
+            if (row0 + u >= M) continue;
+            __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v[u]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float2 f = __bfloat1622float2(p[k]);
-                    p[k] = __floats2bfloat162_rn(gelu_f(f.x + bb[2 * k]), gelu_f(f.y + bb[2 * k + 1]));
-                }
-                y[(size_t)(row0 + u) * C8 + c] = v[u];
+            for (int k = 0; k < 4; ++k) {
+                float2 f = __bfloat1622float2(p[k]);
+                p[k] = __floats2bfloat162_rn(gelu_f(f.x + bb[2 * k]), gelu_f(f.y + bb[2 * k + 1]));
             }
+            y[(size_t)(row0 + u) * C8 + c] = v[u];
         }
     }
 }
 
 // gx = gy * gelu'(x + bias); column sums of gx (= d bias) accumulate per thread, one atomicAdd per column
 // per CTA at the end (g_bias must be zeroed by the caller).
+constexpr int GELU_BWD_RU = 2;
 __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__restrict__ bias, const uint4 *__restrict__ gy,
                                 uint4 *__restrict__ gx, float *__restrict__ g_bias, int M, int C8) {
+    // persistent (the column sums stay in registers, one atomicAdd per column per CTA) and SOFTWARE-PIPELINED: the loads
+    // of iteration i+1 are issued before the math / stores of iteration i, so a warp always has loads in flight.
+    constexpr int RU = GELU_BWD_RU;
+    const int step = gridDim.x * RU;
     for (int c = threadIdx.x; c < C8; c += blockDim.x) {
         float bb[8], acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         load_bias8(bias, c, bb);
-        for (int row0 = blockIdx.x * GELU_RU; row0 < M; row0 += gridDim.x * GELU_RU) {
-            uint4 v[GELU_RU], g[GELU_RU];
+        uint4 v[RU], g[RU], vn[RU], gn[RU];
+        int row0 = blockIdx.x * RU;
 #pragma unroll
-            for (int u = 0; u < GELU_RU; ++u)
-                if (row0 + u < M) { v[u] = x[(size_t)(row0 + u) * C8 + c]; g[u] = gy[(size_t)(row0 + u) * C8 + c]; }
+        for (int u = 0; u < RU; ++u)
+            if (row0 + u < M) { v[u] = x[(size_t)(row0 + u) * C8 + c]; g[u] = gy[(size_t)(row0 + u) * C8 + c]; }
+        for (; row0 < M; row0 += step) {
+            const int nxt = row0 + step;
 #pragma unroll
-            for (int u = 0; u < GELU_RU; ++u) {
+            for (int u = 0; u < RU; ++u)
+                if (nxt + u < M) { vn[u] = x[(size_t)(nxt + u) * C8 + c]; gn[u] = gy[(size_t)(nxt + u) * C8 + c]; }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
                 if (row0 + u >= M) continue;
                 __nv_bfloat162 *p = reinterpret_cast<__nv_bfloat162 *>(&v[u]);
                 __nv_bfloat162 *q = reinterpret_cast<__nv_bfloat162 *>(&g[u]);
@@ -364,6 +375,8 @@ __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__rest
                 }
                 gx[(size_t)(row0 + u) * C8 + c] = v[u];
             }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) { v[u] = vn[u]; g[u] = gn[u]; }
         }
         if (g_bias) {
 #pragma unroll
@@ -379,16 +392,21 @@ __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__rest
 constexpr int PACK_RU = 4;
 __global__ void pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__restrict__ dk, const uint4 *__restrict__ dv,
                                 uint4 *__restrict__ out, float *__restrict__ g_bias, int M, int C8) {
-    const int per_row = 3 * C8;
+    const int per_row = 3 * C8, step = gridDim.x * PACK_RU;
     for (int c = threadIdx.x; c < per_row; c += blockDim.x) {
         const int which = c / C8, cc = c - which * C8;
         const uint4 *src = which == 0 ? dq : (which == 1 ? dk : dv);
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int row0 = blockIdx.x * PACK_RU; row0 < M; row0 += gridDim.x * PACK_RU) {
-            uint4 v[PACK_RU];
+        uint4 v[PACK_RU], vn[PACK_RU];
+        int row0 = blockIdx.x * PACK_RU;
+#pragma unroll
+        for (int u = 0; u < PACK_RU; ++u)
+            if (row0 + u < M) v[u] = src[(size_t)(row0 + u) * C8 + cc];
+        for (; row0 < M; row0 += step) {            // software-pipelined like gelu_bwd_kernel
+            const int nxt = row0 + step;
 #pragma unroll
             for (int u = 0; u < PACK_RU; ++u)
-                if (row0 + u < M) v[u] = src[(size_t)(row0 + u) * C8 + cc];
+                if (nxt + u < M) vn[u] = src[(size_t)(nxt + u) * C8 + cc];
 #pragma unroll
             for (int u = 0; u < PACK_RU; ++u) {
                 if (row0 + u >= M) continue;
@@ -402,12 +420,46 @@ __global__ void pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__res
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < PACK_RU; ++u) v[u] = vn[u];
         }
         if (g_bias) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) atomicAdd(g_bias + c * 8 + k, acc[k]);
         }
     }
+}
+
+// Patch embedding as a GEMM (timm PatchEmbed: Conv2d(kernel = stride = p) -> flatten -> NLC, vision_transformer.py:
+// patch_embed): non-overlapping patches make im2col a pure permutation, so the conv is
+//   tokens[B*gh*gw, D] = patches[B*gh*gw, Cin*p*p] @ W[D, Cin*p*p]^T + b .
+// This kernel writes `patches` in bf16 (GEMM operand) from the fp32 NCHW image: 4 pixels (16 B in, 8 B out) per thread,
+// output-major indexing -> fully coalesced stores, 64-byte-segment loads.  (cuDNN's implicit-GEMM for Cin = 3 pads the
+// channel dimension to 8 and adds two layout conversions: 4.3 ms per step at B = 256 vs 0.1 ms here + a 0.06 ms GEMM.)
+__global__ void patchify_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, int Cin, int H, int W, int p,
+                                size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int p4 = p >> 2, gw = W / p, gh = H / p;
+    size_t t = i;
+    const int kx4 = (int)(t % p4); t /= p4;
+    const int ky = (int)(t % p); t /= p;
+    const int c = (int)(t % Cin); t /= Cin;
+    const int px = (int)(t % gw); t /= gw;
+    const int py = (int)(t % gh); t /= gh;
+    const size_t b = t;
+    const float4 v = *reinterpret_cast<const float4 *>(x + ((b * Cin + c) * H + (size_t)py * p + ky) * W + (size_t)px * p + kx4 * 4);
+    store_bf16x4(out + i * 4, v);
+}
+
+// persistent grids = (SM count) x (CTAs of this kernel that are actually co-resident on one SM)
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem = 0) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sms * per_sm;
 }
 
 static int bwd_grid() {
@@ -478,10 +530,20 @@ int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, 
     const int C8 = C / 8, per_row = 3 * C8;
     const int threads = per_row >= 288 ? 288 : (per_row >= 192 ? 192 : 96);
     const int rows4 = (int)((M + PACK_RU - 1) / PACK_RU);
-    const int grid = rows4 < 148 * 5 ? rows4 : 148 * 5;
+    int grid = persistent_grid(pack_qkv_kernel, threads);
+    if (rows4 < grid) grid = rows4;
     if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * 3 * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
     pack_qkv_kernel<<<grid, threads, 0, st>>>((const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv, (uint4 *)dqkv,
                                               g_bias, (int)M, C8);
+    return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
+}
+
+int xq_vit_patchify(const float *x, void *patches, int B, int Cin, int H, int W, int p, void *stream) {
+    if (!x || !patches || B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || p <= 0) return XQ_ERR_ARG;
+    if ((p & 3) || H % p || W % p) return XQ_ERR_UNSUPPORTED;
+    const size_t total4 = (size_t)B * Cin * H * W / 4;
+    patchify_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)patches, Cin, H, W,
+                                                                                       p, total4);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
@@ -489,7 +551,7 @@ int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, voi
     if (!x || !y || M <= 0 || C <= 0 || (C & 7)) return XQ_ERR_ARG;
     int C8 = C / 8;
     int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
-    int grid = (M + GELU_RU - 1) / GELU_RU < 148 * 4 ? (M + GELU_RU - 1) / GELU_RU : 148 * 4;
+    int grid = (M + GELU_RU - 1) / GELU_RU;
     gelu_fwd_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const uint4 *)x, bias, (uint4 *)y, M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
@@ -499,7 +561,8 @@ int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, 
     cudaStream_t st = (cudaStream_t)stream;
     int C8 = C / 8;
     int threads = C8 >= 384 ? 384 : (C8 >= 192 ? 192 : 128);
-    int grid = (M + GELU_RU - 1) / GELU_RU < 148 * 4 ? (M + GELU_RU - 1) / GELU_RU : 148 * 4;
+    int grid = persistent_grid(gelu_bwd_kernel, threads);
+    if ((M + GELU_BWD_RU - 1) / GELU_BWD_RU < grid) grid = (M + GELU_BWD_RU - 1) / GELU_BWD_RU;
     if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
     gelu_bwd_kernel<<<grid, threads, 0, st>>>((const uint4 *)x, bias, (const uint4 *)gy, (uint4 *)gx, g_bias, M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;

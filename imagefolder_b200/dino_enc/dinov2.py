@@ -12,7 +12,7 @@ import math
 import torch
 import torch.nn as nn
 
-from ..vit_ops import run_blocks
+from ..vit_ops import patch_embed, run_blocks
 from .to_pixel import ToPixel
 from .vision_transformer import Attention, create_model, trunc_normal_
 
@@ -92,7 +92,7 @@ class DINOv2Encoder(nn.Module):
 
     def forward(self, x, masks=None):
         """dinov2.py:146-198 -> [B, num_latent_tokens, D]"""
-        x = self.model.patch_embed(x)
+        x = patch_embed(self.model.patch_embed, x)
         with _autocast_off(x):
             x = self.model._pos_embed(x)
             x = self.model.patch_drop(x)

@@ -41,7 +41,8 @@ class _ResidualLN(torch.autograd.Function):
         L = C.lib()
         C.call("xq_vit_residual_ln_fwd", 1, L.xq_vit_residual_ln_fwd, C.ptr(x), C.ptr(branch), C.ptr(branch_bias),
                C.ptr(ls_gamma), C.ptr(rowscale), S, C.ptr(ln_w), C.ptr(ln_b), float(eps), M, D, C.ptr(x_out), C.ptr(y),
-               C.ptr(mean), C.ptr(rstd), C.stream_ptr(x.device))
+               C.ptr(mean), C.ptr(rstd), C.stream_ptr(x.device),
+               nbytes=M * D * (10 + (2 if branch is not None else 0)))
         ctx.save_for_backward(x_out, mean, rstd, ln_w, branch, branch_bias, ls_gamma, rowscale)
         ctx.shape = (Bn, S, D)
         ctx.set_materialize_grads(False)
@@ -72,7 +73,9 @@ class _ResidualLN(torch.autograd.Function):
         C.call("xq_vit_residual_ln_bwd", 2, L.xq_vit_residual_ln_bwd, C.ptr(g_xout), C.ptr(g_y), C.ptr(x_out),
                C.ptr(mean), C.ptr(rstd), C.ptr(ln_w), C.ptr(branch), C.ptr(branch_bias), C.ptr(ls_gamma),
                C.ptr(rowscale), S, M, D, C.ptr(g_x), C.ptr(g_branch), C.ptr(g_w), C.ptr(g_b), C.ptr(g_g), C.ptr(g_bb),
-               C.ptr(ws), ws.numel(), C.stream_ptr(dev))
+               C.ptr(ws), ws.numel(), C.stream_ptr(dev),
+               nbytes=M * D * (8 + (4 if g_xout is not None else 0) + (2 if g_y is not None else 0)
+                               + (4 if branch is not None else 0)))
         return g_x, g_branch, g_bb, g_g, None, g_w, g_b, None
 
 
@@ -90,7 +93,8 @@ class _GeluBias(torch.autograd.Function):
         M = x.numel() // Cc
         y = torch.empty_like(x)
         L = C.lib()
-        C.call("xq_vit_gelu_fwd", 1, L.xq_vit_gelu_fwd, C.ptr(x), C.ptr(bias), C.ptr(y), M, Cc, C.stream_ptr(x.device))
+        C.call("xq_vit_gelu_fwd", 1, L.xq_vit_gelu_fwd, C.ptr(x), C.ptr(bias), C.ptr(y), M, Cc, C.stream_ptr(x.device),
+               nbytes=M * Cc * 4)
         ctx.save_for_backward(x, bias)
         return y
 
@@ -106,7 +110,7 @@ class _GeluBias(torch.autograd.Function):
         gb = torch.empty_like(bias) if bias is not None else None
         L = C.lib()
         C.call("xq_vit_gelu_bwd", 1, L.xq_vit_gelu_bwd, C.ptr(x), C.ptr(bias), C.ptr(gy), C.ptr(gx), C.ptr(gb), M, Cc,
-               C.stream_ptr(x.device))
+               C.stream_ptr(x.device), nbytes=M * Cc * 6)
         return gx, gb
 
 
@@ -142,7 +146,7 @@ def _sdpa_packed_backward(inner, dims, g, want_bias_grad: bool):
             db = torch.empty(3 * C, dtype=torch.float32, device=dq.device)
         L = _lib()
         _call("xq_vit_pack_qkv", 1, L.xq_vit_pack_qkv, _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(dqkv),
-              _ptr(db) if db is not None else None, B * N, C, _stream(dq.device))
+              _ptr(db) if db is not None else None, B * N, C, _stream(dq.device), nbytes=B * N * C * 12)
     else:  # layout the library did not produce in our runs; keep correctness
         torch.stack([t.reshape(B, N, C) for t in flat], dim=2, out=dqkv.view(B, N, 3, C))
         if want_bias_grad:
@@ -213,6 +217,58 @@ def attention_forward(attn, y):
     else:
         o = packed_attention(attn.qkv(y), attn.num_heads, p)
     return F.linear(o, attn.proj.weight)      # the proj bias is folded into the next residual_ln
+
+
+class _PatchEmbed(torch.autograd.Function):
+    """timm PatchEmbed (Conv2d(kernel = stride = p) -> flatten(2).transpose(1,2)) as im2col-permutation + ONE GEMM.
+    x fp32 [B,Cin,H,W] (no gradient), W [D,Cin,p,p] / b [D] fp32 parameters -> tokens bf16 [B, gh*gw, D]."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        Bn, Cin, H, Wd = x.shape
+        D, p = W.shape[0], W.shape[2]
+        x = x.contiguous()
+        M, K = Bn * (H // p) * (Wd // p), Cin * p * p
+        patches = torch.empty(M, K, dtype=torch.bfloat16, device=x.device)
+        L = _lib()
+        _call("xq_vit_patchify", 1, L.xq_vit_patchify, _ptr(x), _ptr(patches), Bn, Cin, H, Wd, p, _stream(x.device),
+              nbytes=x.numel() * 6)
+        Wb = W.reshape(D, K).to(torch.bfloat16)
+        if b is not None:
+            y = torch.addmm(b.to(torch.bfloat16), patches, Wb.t())
+        else:
+            y = patches @ Wb.t()
+        ctx.save_for_backward(patches)
+        ctx.wshape = tuple(W.shape)
+        ctx.has_bias = b is not None
+        return y.view(Bn, M // Bn, D)
+
+    @staticmethod
+    def backward(ctx, g):
+        (patches,) = ctx.saved_tensors
+        D = ctx.wshape[0]
+        g2 = g.reshape(-1, D)
+        if g2.dtype != torch.bfloat16:
+            g2 = g2.to(torch.bfloat16)
+        dW = (g2.t() @ patches).float().view(ctx.wshape) if ctx.needs_input_grad[1] else None
+        db = g2.float().sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return None, dW, db
+
+
+def patch_embed_ok(pe, x) -> bool:
+    p = pe.patch_size[0]
+    return (x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16 and isinstance(pe.norm, nn.Identity)
+            and pe.patch_size[0] == pe.patch_size[1] and p % 4 == 0 and x.shape[2] % p == 0 and x.shape[3] % p == 0
+            and tuple(pe.proj.stride) == tuple(pe.proj.kernel_size) and tuple(pe.proj.padding) == (0, 0))
+
+
+def patch_embed(pe, x):
+    """PatchEmbed.forward on the fused path when it applies (bf16 autocast, fp32 CUDA image that needs no gradient,
+    patch % 4 == 0, no norm); otherwise the module's own conv."""
+    if patch_embed_ok(pe, x):
+        return _PatchEmbed.apply(x, pe.proj.weight, pe.proj.bias)
+    return pe(x)
 
 
 def _droppath_scale(mod, batch: int, device):

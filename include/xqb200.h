@@ -214,6 +214,10 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
  *   receives the column sums of dqkv = the gradient of the qkv bias (nn.Linear's backward `sum(0)` pass, fused). */
 int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, float *g_bias, size_t M, int C,
                     void *stream);
+/*   im2col of the patch embedding (timm PatchEmbed = Conv2d(kernel = stride = p), vision_transformer.py PatchEmbed.forward):
+ *   x fp32 [B,Cin,H,W] -> patches bf16 [B*(H/p)*(W/p), Cin*p*p] (K index = (c*p + ky)*p + kx = the flattened conv
+ *   weight), so that tokens = patches @ weight.view(D,-1)^T + bias is a plain GEMM.  p % 4 == 0, H % p == W % p == 0. */
+int xq_vit_patchify(const float *x, void *patches, int B, int Cin, int H, int W, int p, void *stream);
 /*   y = GELU(x + bias) exact-erf form (timm Mlp act_layer=nn.GELU), x / y bf16 [M,C], bias fp32 [C] or NULL,
  *   C % 8 == 0.  Backward also returns g_bias [C] = column sums of gx (may be NULL). */
 int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, void *stream);

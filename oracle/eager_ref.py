@@ -199,8 +199,8 @@ class EagerTokenizer(torch.nn.Module):
     def forward(self, x, epoch, alpha, beta, delta):
         from imagefolder_b200 import vit_ops
         m = self.m
-        saved = vit_ops.fused_path_ok
-        vit_ops.fused_path_ok = lambda *a, **k: False
+        saved, saved_pe = vit_ops.fused_path_ok, vit_ops.patch_embed_ok
+        vit_ops.fused_path_ok = vit_ops.patch_embed_ok = lambda *a, **k: False
         try:
             h = m.encode(x)
             b, c, l, _ = h.shape
@@ -227,5 +227,5 @@ class EagerTokenizer(torch.nn.Module):
                 en = 0.0
             dec = m.decode(quant)
         finally:
-            vit_ops.fused_path_ok = saved
+            vit_ops.fused_path_ok, vit_ops.patch_embed_ok = saved, saved_pe
         return dec, (vq, cm, en, usages), None, None, 0.0

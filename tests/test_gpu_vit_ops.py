@@ -187,3 +187,43 @@ def test_pack_qkv_cabi_ragged_rows_and_bias():
                                       _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
         assert torch.equal(out, ref)
     assert L.xq_vit_pack_qkv(None, None, None, None, None, 4, 8, None) != 0
+
+
+def test_patch_embed_gemm_matches_conv():
+    """_PatchEmbed (patchify kernel + GEMM) vs the module's Conv2d under the same bf16 autocast; patchify itself is a
+    pure permutation -> bit-exact against unfold."""
+    from imagefolder_b200 import _capi
+    from imagefolder_b200.dino_enc.vision_transformer import PatchEmbed
+    from imagefolder_b200.vit_ops import patch_embed, patch_embed_ok
+    torch.manual_seed(8)
+    for B, Cin, HW, p, D in [(3, 3, 64, 16, 96), (2, 3, 256, 16, 768), (1, 4, 48, 8, 40), (2, 3, 56, 4, 64)]:
+        pe = PatchEmbed(img_size=HW, patch_size=p, in_chans=Cin, embed_dim=D).cuda()
+        x = torch.rand(B, Cin, HW, HW, device="cuda") * 2 - 1
+        patches = torch.empty(B * (HW // p) ** 2, Cin * p * p, device="cuda", dtype=torch.bfloat16)
+        L = _capi.lib()
+        _capi.check(L.xq_vit_patchify(_capi.ptr(x), _capi.ptr(patches), B, Cin, HW, HW, p, _capi.stream_ptr(x.device)),
+                    "xq_vit_patchify")
+        ref = torch.nn.functional.unfold(x, kernel_size=p, stride=p).transpose(1, 2).reshape(patches.shape)
+        assert torch.equal(patches, ref.to(torch.bfloat16))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert patch_embed_ok(pe, x)
+            y1 = patch_embed(pe, x)
+            y2 = pe(x)
+        assert y1.shape == y2.shape and y1.dtype == torch.bfloat16
+        np.testing.assert_allclose(y1.detach().float().cpu().numpy(), y2.detach().float().cpu().numpy(), rtol=2e-2, atol=2e-2)
+        g = torch.randn_like(y1)
+        gW1, gb1 = torch.autograd.grad(y1, (pe.proj.weight, pe.proj.bias), g)
+        gW2, gb2 = torch.autograd.grad(y2, (pe.proj.weight, pe.proj.bias), g)
+        assert gW1.dtype == torch.float32 and gW1.shape == pe.proj.weight.shape
+        sW, sb = float(gW2.abs().max()), float(gb2.abs().max())
+        np.testing.assert_allclose(gW1.cpu().numpy(), gW2.cpu().numpy(), rtol=2e-2, atol=2e-2 * sW)
+        np.testing.assert_allclose(gb1.cpu().numpy(), gb2.cpu().numpy(), rtol=2e-2, atol=2e-2 * sb)
+    # not applicable (image needs a gradient / no autocast) -> the module's own conv
+    xg = torch.rand(1, 3, 64, 64, device="cuda", requires_grad=True)
+    pe = PatchEmbed(img_size=64, patch_size=16, in_chans=3, embed_dim=32).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert not patch_embed_ok(pe, xg)
+    assert not patch_embed_ok(pe, xg.detach())
+    L = _capi.lib()
+    assert L.xq_vit_patchify(None, None, 1, 3, 64, 64, 16, None) != 0
+    assert L.xq_vit_patchify(_capi.ptr(xg.detach()), _capi.ptr(xg.detach()), 1, 3, 64, 64, 6, None) != 0
