@@ -120,124 +120,198 @@ residual_ln_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restr
     }
 }
 
-// Backward.  Persistent grid; each warp walks rows with a grid stride, RPW = 2 rows per iteration so that twice as
-// many loads are in flight (the kernel is bound by global-load latency: long-scoreboard stalls dominate at 16 warps/SM).
-// The four column partial sums (d ln_w, d ln_b, sum G*s*branch, sum G*s) live in a per-warp SHARED-MEMORY accumulator
-// (each lane owns its columns -> plain load-add-store, no atomics).  CTA partials -> part[blockIdx][4][D].
+// ---- TMA-bulk staged streaming skeleton -------------------------------------------------------------------------
+// tools/mb/stream_mb.cu (B200): a persistent 1-CTA-per-SM kernel whose producer warp stages row tiles into shared memory
+// with cp.async.bulk (1-D TMA, mbarrier complete_tx) and whose consumer warps each own one row of the tile, with tiles
+// handed out by an atomic counter, streams at 6.7-6.8 TB/s INCLUDING register-resident column sums -- the same rate as a
+// flat copy -- where the best register-load loop (grid-stride, software-pipelined) reaches 5.7-6.0 and the previous
+// warp-per-row LayerNorm backward 4.5.  No registers are spent on loads in flight and the memory system always has
+// NST-1 tiles outstanding.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tXQV_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XQV_DONE;\n\tbra XQV_WAIT;\n\tXQV_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Backward.  grid = #SMs, 1 CTA / SM, warp 0 = producer, LNB_TR consumer warps (one tile row each), LNB_NST stages.
+// Stage layout: x_out [TR][D] f32 | g_xout [TR][D] f32 | g_y [TR][D] bf16 | branch [TR][D] bf16 | mean, rstd, scale [TR].
+// A lane owns columns (i*32 + lane)*4 .. +3, i < NV, for EVERY row it sees, so ln_w / ls_gamma and the four column
+// partial sums (d ln_w, d ln_b, sum G*s*branch, sum G*s) live in registers for the whole kernel.
 //   g_xout may be null (no later residual gradient), g_y may be null (LN output unused).
 constexpr int NACC = 4;
-constexpr int RPW = 2;
+constexpr int LNB_TR = 8;
+constexpr int LNB_THREADS = (LNB_TR + 1) * 32;
+__host__ __device__ inline size_t lnb_stage_bytes(int D) { return (size_t)LNB_TR * D * 12 + 128; }
+__host__ __device__ inline int lnb_stages(int D) { return lnb_stage_bytes(D) * 3 <= 225 * 1024 ? 3 : 2; }
+
 template <int NV>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(LNB_THREADS, 1)
 residual_ln_bwd_kernel(const float *__restrict__ g_xout, const __nv_bfloat16 *__restrict__ g_y,
                        const float *__restrict__ x_out, const float *__restrict__ mean_in,
                        const float *__restrict__ rstd_in, const float *__restrict__ ln_w,
                        const __nv_bfloat16 *__restrict__ branch, const float *__restrict__ branch_bias,
                        const float *__restrict__ ls_gamma, const float *__restrict__ rowscale, int rows_per_sample,
                        int M, float *__restrict__ g_x, __nv_bfloat16 *__restrict__ g_branch,
-                       float *__restrict__ part) {
+                       float *__restrict__ part, int *__restrict__ counter, int nst) {
     constexpr int D = NV * 128;
-    extern __shared__ __align__(16) float acc_s[];  // [WARPS][NACC][D]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *acc = acc_s + (size_t)warp * NACC * D;
-    for (int i = lane * 4; i < NACC * D; i += 128) *reinterpret_cast<float4 *>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    const int stride = gridDim.x * WARPS;
-    for (int row0 = blockIdx.x * WARPS + warp; row0 < M; row0 += stride * RPW) {
-        int rows[RPW];
-        bool ok[RPW];
-        float mean[RPW], rstd[RPW], sc[RPW], c1[RPW], c2[RPW];
-        float4 xh[RPW][NV], gy[RPW][NV];
-#pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            rows[u] = row0 + u * stride;
-            ok[u] = rows[u] < M;
-            const int r = ok[u] ? rows[u] : row0;
-            mean[u] = mean_in[r];
-            rstd[u] = rstd_in[r];
-            sc[u] = (branch && rowscale) ? rowscale[r / rows_per_sample] : 1.f;
-            c1[u] = c2[u] = 0.f;
-        }
-        // phase 1: issue the loads of both rows back to back, then the per-row statistics
-#pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            const size_t base = (size_t)(ok[u] ? rows[u] : row0) * D;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int col = (i * 32 + lane) * 4;
-                xh[u][i] = *reinterpret_cast<const float4 *>(x_out + base + col);
-                gy[u][i] = g_y ? load_bf16x4(g_y + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int TR = LNB_TR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[3], empty[3];
+    __shared__ int tile_of[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (M + TR - 1) / TR;
+    const size_t stage_bytes = lnb_stage_bytes(D);
+    auto st_x = [&](int st) { return reinterpret_cast<float *>(smem + st * stage_bytes); };
+    auto st_r = [&](int st) { return reinterpret_cast<float *>(smem + st * stage_bytes + (size_t)TR * D * 4); };
+    auto st_gy = [&](int st) { return reinterpret_cast<__nv_bfloat16 *>(smem + st * stage_bytes + (size_t)TR * D * 8); };
+    auto st_br = [&](int st) { return reinterpret_cast<__nv_bfloat16 *>(smem + st * stage_bytes + (size_t)TR * D * 10); };
+    auto st_sc = [&](int st) { return reinterpret_cast<float *>(smem + st * stage_bytes + (size_t)TR * D * 12); };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], TR); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        for (int it = 0;; ++it) {
+            const int st = it % nst;
+            mbar_wait(&empty[st], ((it / nst) & 1) ^ 1);
+            int tile = 0;
+            if (lane == 0) tile = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(counter, 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= ntiles) {
+                if (lane == 0) { tile_of[st] = tile; mbar_arrive(&full[st]); mbar_arrive(&full[st]); }
+                break;
             }
+            const int r0 = tile * TR, nr = min(TR, M - r0);
+            if (lane == 0) {
+                tile_of[st] = tile;
+                const uint32_t b4 = (uint32_t)nr * D * 4, b2 = (uint32_t)nr * D * 2;
+                mbar_expect_tx(&full[st], b4 + (g_xout ? b4 : 0) + (g_y ? b2 : 0) + (branch ? b2 : 0));
+                bulk_g2s(st_x(st), x_out + (size_t)r0 * D, b4, &full[st]);
+                if (g_y) bulk_g2s(st_gy(st), g_y + (size_t)r0 * D, b2, &full[st]);
+                if (g_xout) bulk_g2s(st_r(st), g_xout + (size_t)r0 * D, b4, &full[st]);
+                if (branch) bulk_g2s(st_br(st), branch + (size_t)r0 * D, b2, &full[st]);
+            }
+            if (lane < nr) {
+                float *sc = st_sc(st);
+                sc[lane] = mean_in[r0 + lane];
+                sc[TR + lane] = rstd_in[r0 + lane];
+                sc[2 * TR + lane] = (branch && rowscale) ? rowscale[(r0 + lane) / rows_per_sample] : 1.f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
         }
+    } else {
+        // ---------------- consumers ----------------
+        const int cw = warp - 1;
+        float4 w4[NV], gm4[NV], a0[NV], a1[NV], a2[NV], a3[NV];
 #pragma unroll
-        for (int u = 0; u < RPW; ++u) {
+        for (int i = 0; i < NV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            w4[i] = g_y ? *reinterpret_cast<const float4 *>(ln_w + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gm4[i] = (branch && ls_gamma) ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+            a0[i] = a1[i] = a2[i] = a3[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int it = 0;; ++it) {
+            const int st = it % nst;
+            mbar_wait(&full[st], (it / nst) & 1);
+            const int tile = tile_of[st];
+            if (tile >= ntiles) break;
+            const int row = tile * TR + cw;
+            if (row < M) {
+                const float *sc = st_sc(st);
+                const float mean = sc[cw], rstd = sc[TR + cw], s_row = sc[2 * TR + cw];
+                const float *xs = st_x(st) + (size_t)cw * D;
+                const float *rs = st_r(st) + (size_t)cw * D;
+                const __nv_bfloat16 *gys = st_gy(st) + (size_t)cw * D;
+                const __nv_bfloat16 *brs = st_br(st) + (size_t)cw * D;
+                // two passes over the row in SHARED memory (x-hat and g*w are recomputed in pass 2 instead of being kept
+                // in 48 more registers; shared-memory bandwidth is nowhere near binding here)
+                float c1 = 0.f, c2 = 0.f;
+                if (g_y) {
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int col = (i * 32 + lane) * 4;
-                float4 xv = xh[u][i];
-                xh[u][i] = make_float4((xv.x - mean[u]) * rstd[u], (xv.y - mean[u]) * rstd[u], (xv.z - mean[u]) * rstd[u],
-                                       (xv.w - mean[u]) * rstd[u]);
-                if (g_y && ok[u]) {
-                    float4 g = gy[u][i];
-                    float4 w = *reinterpret_cast<const float4 *>(ln_w + col);
-                    float4 a0 = *reinterpret_cast<float4 *>(acc + 0 * D + col);
-                    float4 a1 = *reinterpret_cast<float4 *>(acc + 1 * D + col);
-                    a0.x += g.x * xh[u][i].x; a0.y += g.y * xh[u][i].y; a0.z += g.z * xh[u][i].z; a0.w += g.w * xh[u][i].w;
-                    a1.x += g.x; a1.y += g.y; a1.z += g.z; a1.w += g.w;
-                    *reinterpret_cast<float4 *>(acc + 0 * D + col) = a0;
-                    *reinterpret_cast<float4 *>(acc + 1 * D + col) = a1;
-                    gy[u][i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
-                    c1[u] += gy[u][i].x + gy[u][i].y + gy[u][i].z + gy[u][i].w;
-                    c2[u] += gy[u][i].x * xh[u][i].x + gy[u][i].y * xh[u][i].y + gy[u][i].z * xh[u][i].z + gy[u][i].w * xh[u][i].w;
+                    for (int i = 0; i < NV; ++i) {
+                        const int col = (i * 32 + lane) * 4;
+                        const float4 xv = *reinterpret_cast<const float4 *>(xs + col);
+                        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                                                      (xv.w - mean) * rstd);
+                        const float4 g = load_bf16x4(gys + col);
+                        a0[i].x += g.x * xh.x; a0[i].y += g.y * xh.y; a0[i].z += g.z * xh.z; a0[i].w += g.w * xh.w;
+                        a1[i].x += g.x; a1[i].y += g.y; a1[i].z += g.z; a1[i].w += g.w;
+                        const float4 gw = make_float4(g.x * w4[i].x, g.y * w4[i].y, g.z * w4[i].z, g.w * w4[i].w);
+                        c1 += gw.x + gw.y + gw.z + gw.w;
+                        c2 += gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w;
+                    }
+                    c1 = warp_sum(c1) * (1.f / D);
+                    c2 = warp_sum(c2) * (1.f / D);
+                }
+                const size_t base = (size_t)row * D;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int col = (i * 32 + lane) * 4;
+                    float4 G = g_xout ? *reinterpret_cast<const float4 *>(rs + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g_y) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(xs + col);
+                        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd,
+                                                      (xv.w - mean) * rstd);
+                        const float4 g = load_bf16x4(gys + col);
+                        G.x += rstd * (g.x * w4[i].x - c1 - xh.x * c2);
+                        G.y += rstd * (g.y * w4[i].y - c1 - xh.y * c2);
+                        G.z += rstd * (g.z * w4[i].z - c1 - xh.z * c2);
+                        G.w += rstd * (g.w * w4[i].w - c1 - xh.w * c2);
+                    }
+                    if (g_x) *reinterpret_cast<float4 *>(g_x + base + col) = G;
+                    if (branch) {
+                        const float4 bv = load_bf16x4(brs + col);
+                        const float4 Gs = make_float4(G.x * s_row, G.y * s_row, G.z * s_row, G.w * s_row);
+                        a2[i].x += Gs.x * bv.x; a2[i].y += Gs.y * bv.y; a2[i].z += Gs.z * bv.z; a2[i].w += Gs.w * bv.w;
+                        a3[i].x += Gs.x; a3[i].y += Gs.y; a3[i].z += Gs.z; a3[i].w += Gs.w;
+                        if (g_branch)
+                            store_bf16x4(g_branch + base + col,
+                                         make_float4(Gs.x * gm4[i].x, Gs.y * gm4[i].y, Gs.z * gm4[i].z, Gs.w * gm4[i].w));
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
         }
+        // park the register sums in the stage memory -- but only once EVERY consumer warp is past its last real tile
+        // (a fast warp sees the sentinel while a slow one still reads its row): named barrier over the consumer warps
+        asm volatile("bar.sync 1, %0;" ::"n"(LNB_TR * 32) : "memory");
+        float *red = reinterpret_cast<float *>(smem) + (size_t)cw * NACC * D;
 #pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            c1[u] = warp_sum(c1[u]) * (1.f / D);
-            c2[u] = warp_sum(c2[u]) * (1.f / D);
-        }
-        // phase 2
-#pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            if (!ok[u]) continue;
-            const size_t base = (size_t)rows[u] * D;
-            float4 rr[NV], bv[NV];
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int col = (i * 32 + lane) * 4;
-                rr[i] = g_xout ? *reinterpret_cast<const float4 *>(g_xout + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                bv[i] = branch ? load_bf16x4(branch + base + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int col = (i * 32 + lane) * 4;
-                float4 G;
-                G.x = rstd[u] * (gy[u][i].x - c1[u] - xh[u][i].x * c2[u]) + rr[i].x;
-                G.y = rstd[u] * (gy[u][i].y - c1[u] - xh[u][i].y * c2[u]) + rr[i].y;
-                G.z = rstd[u] * (gy[u][i].z - c1[u] - xh[u][i].z * c2[u]) + rr[i].z;
-                G.w = rstd[u] * (gy[u][i].w - c1[u] - xh[u][i].w * c2[u]) + rr[i].w;
-                if (g_x) *reinterpret_cast<float4 *>(g_x + base + col) = G;
-                if (branch) {
-                    float4 gm = ls_gamma ? *reinterpret_cast<const float4 *>(ls_gamma + col) : make_float4(1.f, 1.f, 1.f, 1.f);
-                    float4 a2 = *reinterpret_cast<float4 *>(acc + 2 * D + col);
-                    float4 a3 = *reinterpret_cast<float4 *>(acc + 3 * D + col);
-                    float4 Gs = make_float4(G.x * sc[u], G.y * sc[u], G.z * sc[u], G.w * sc[u]);
-                    a2.x += Gs.x * bv[i].x; a2.y += Gs.y * bv[i].y; a2.z += Gs.z * bv[i].z; a2.w += Gs.w * bv[i].w;
-                    a3.x += Gs.x; a3.y += Gs.y; a3.z += Gs.z; a3.w += Gs.w;
-                    *reinterpret_cast<float4 *>(acc + 2 * D + col) = a2;
-                    *reinterpret_cast<float4 *>(acc + 3 * D + col) = a3;
-                    if (g_branch) store_bf16x4(g_branch + base + col, make_float4(Gs.x * gm.x, Gs.y * gm.y, Gs.z * gm.z, Gs.w * gm.w));
-                }
-            }
+        for (int i = 0; i < NV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            *reinterpret_cast<float4 *>(red + 0 * D + col) = a0[i];
+            *reinterpret_cast<float4 *>(red + 1 * D + col) = a1[i];
+            *reinterpret_cast<float4 *>(red + 2 * D + col) = a2[i];
+            *reinterpret_cast<float4 *>(red + 3 * D + col) = a3[i];
         }
     }
     __syncthreads();
+    const float *red = reinterpret_cast<const float *>(smem);
     float *outp = part + (size_t)blockIdx.x * NACC * D;
-    for (int e = threadIdx.x; e < NACC * D; e += THREADS) {
+    for (int e = threadIdx.x; e < NACC * D; e += blockDim.x) {
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) a += acc_s[(size_t)w * NACC * D + e];
+        for (int w = 0; w < TR; ++w) a += red[(size_t)w * NACC * D + e];
         outp[e] = a;
     }
 }
@@ -466,7 +540,7 @@ static int bwd_grid() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 2;  // 2 CTAs / SM (shared-memory accumulators: 96 KB per CTA at D=768)
+    return sms;      // 1 CTA / SM (TMA-staged tiles fill the shared memory)
 }
 
 }  // namespace xqv
@@ -483,7 +557,7 @@ using namespace xqv;
 
 extern "C" {
 
-size_t xq_vit_ln_bwd_workspace_bytes(int D) { return sizeof(float) * (size_t)bwd_grid() * NACC * D; }
+size_t xq_vit_ln_bwd_workspace_bytes(int D) { return sizeof(float) * (size_t)bwd_grid() * NACC * D + 256; }
 
 int xq_vit_residual_ln_fwd(const float *x, const void *branch, const float *branch_bias, const float *ls_gamma,
                            const float *rowscale, int rows_per_sample, const float *ln_w, const float *ln_b, float eps,
@@ -505,17 +579,24 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
                            void *workspace, size_t workspace_bytes, void *stream) {
     if (!x_out || !mean || !rstd || M <= 0 || !workspace) return XQ_ERR_ARG;
     if (g_y && !ln_w) return XQ_ERR_ARG;
-    const int grid = bwd_grid();
-    if (workspace_bytes < sizeof(float) * (size_t)grid * NACC * D) return XQ_ERR_WORKSPACE;
+    if (branch && rowscale && rows_per_sample <= 0) return XQ_ERR_ARG;
+    int grid = bwd_grid();
+    if (workspace_bytes < sizeof(float) * (size_t)grid * NACC * D + 256) return XQ_ERR_WORKSPACE;
+    const int ntiles = (M + LNB_TR - 1) / LNB_TR;
+    if (grid > ntiles) grid = ntiles;
     cudaStream_t st = (cudaStream_t)stream;
     float *part = (float *)workspace;
-    const size_t smem = sizeof(float) * (size_t)WARPS * NACC * D;
+    int *counter = (int *)((char *)workspace + sizeof(float) * (size_t)bwd_grid() * NACC * D);   // dynamic tile counter
+    if (cudaMemsetAsync(counter, 0, sizeof(int), st) != cudaSuccess) return XQ_ERR_CUDA;
+    const int nst = lnb_stages(D);
+    size_t smem = lnb_stage_bytes(D) * nst;
+    if (smem < sizeof(float) * (size_t)LNB_TR * NACC * D) smem = sizeof(float) * (size_t)LNB_TR * NACC * D;
     XQV_DISPATCH(D, {
         if (cudaFuncSetAttribute(residual_ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return XQ_ERR_CUDA;
-        residual_ln_bwd_kernel<NV><<<grid, THREADS, smem, st>>>(
+        residual_ln_bwd_kernel<NV><<<grid, LNB_THREADS, smem, st>>>(
             g_xout, (const __nv_bfloat16 *)g_y, x_out, mean, rstd, ln_w, (const __nv_bfloat16 *)branch, branch_bias,
-            ls_gamma, rowscale, rows_per_sample, M, g_x, (__nv_bfloat16 *)g_branch, part);
+            ls_gamma, rowscale, rows_per_sample, M, g_x, (__nv_bfloat16 *)g_branch, part, counter, nst);
     });
     if (cudaGetLastError() != cudaSuccess) return XQ_ERR_CUDA;
     reduce_parts_kernel<<<(D + 31) / 32, 256, 0, st>>>(part, grid, D, ls_gamma, branch_bias, g_ln_w, g_ln_b,

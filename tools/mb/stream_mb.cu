@@ -158,6 +158,109 @@ __global__ void k_colown_dyn(const uint4 *__restrict__ a, uint4 *__restrict__ o,
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(colsum + c * 8 + k, acc[k]);
 }
+// (7) TMA-bulk staged, persistent, dynamically scheduled: warp 0 = producer (cp.async.bulk 1-D, mbarrier complete_tx),
+//     NCW consumer warps each own one row of the TR-row tile; column sums in registers (lane owns its columns).
+#include <cstdint>
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+template <int TR, int NST, bool SUM>
+__global__ void __launch_bounds__((TR + 1) * 32)
+k_tma(const uint4 *__restrict__ a, uint4 *__restrict__ o, float *__restrict__ colsum, int *counter, int M, int C8) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[NST], empty[NST];
+    __shared__ int tile_of[NST];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (M + TR - 1) / TR;
+    const uint32_t row_bytes = (uint32_t)C8 * 16;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TR); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0;; ++it) {
+                const int st = it % NST;
+                mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                const int tile = it == 0 ? blockIdx.x : atomicAdd(counter, 1);
+                tile_of[st] = tile;
+                if (tile >= ntiles) { mbar_arrive(&full[st]); break; }
+                const int r0 = tile * TR, nr = min(TR, M - r0);
+                mbar_expect_tx(&full[st], nr * row_bytes);
+                bulk_g2s(smem + (size_t)st * TR * row_bytes, a + (size_t)r0 * C8, nr * row_bytes, &full[st]);
+            }
+        }
+    } else {
+        const int cw = warp - 1;
+        float acc[12][8];
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+        for (int it = 0;; ++it) {
+            const int st = it % NST;
+            mbar_wait(&full[st], (it / NST) & 1);
+            const int tile = tile_of[st];
+            if (tile >= ntiles) break;
+            const int row = tile * TR + cw;
+            if (row < M) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(smem + ((size_t)st * TR + cw) * row_bytes);
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    const int c = j * 32 + lane;
+                    if (c < C8) {
+                        uint4 v = src[c];
+                        o[(size_t)row * C8 + c] = v;
+                        if (SUM) {
+                            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(p[k]); acc[j][2 * k] += f.x; acc[j][2 * k + 1] += f.y; }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        if (SUM) {     // per-warp register sums -> smem (the stage buffers are free now) -> ONE atomic per column per CTA
+            float *red = reinterpret_cast<float *>(smem) + (size_t)cw * C8 * 8;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int c = j * 32 + lane;
+                if (c < C8)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) red[c * 8 + k] = acc[j][k];
+            }
+        }
+    }
+    if (SUM) {
+        __syncthreads();
+        const float *red = reinterpret_cast<const float *>(smem);
+        for (int e = threadIdx.x; e < C8 * 8; e += blockDim.x) {
+            float t = 0.f;
+            for (int w = 0; w < TR; ++w) t += red[(size_t)w * C8 * 8 + e];
+            atomicAdd(colsum + e, t);
+        }
+    }
+}
 // (5) gelu on the simple skeletons
 template <int RU>
 __global__ void k_gelu_persist(const uint4 *__restrict__ a, uint4 *__restrict__ o, int M, int C8) {
@@ -244,6 +347,20 @@ int main() {
             init = g * 2;
             snprintf(nm, 64, "DYN RU2 copy+colsum grid %d", g);
             rep(nm, timeit([&] { cudaMemcpyAsync(ctr, &init, 4, cudaMemcpyHostToDevice, 0); k_colown_dyn<2, true, false><<<g, thr>>>(a, o, cs, ctr, M, C8); }));
+        }
+        {
+            auto run = [&](auto kern, int TR, int NST, const char *nm) {
+                size_t sm = (size_t)NST * TR * C8 * 16;
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                int init = 148;
+                rep(nm, timeit([&] { cudaMemcpyAsync(ctr, &init, 4, cudaMemcpyHostToDevice, 0); kern<<<148, (TR + 1) * 32, sm>>>(a, o, cs, ctr, M, C8); }));
+                CK(cudaGetLastError());
+            };
+            run(k_tma<8, 3, false>, 8, 3, "TMA-bulk TR8 x3 stages copy");
+            run(k_tma<8, 3, true>, 8, 3, "TMA-bulk TR8 x3 stages copy+colsum");
+            run(k_tma<8, 4, true>, 8, 4, "TMA-bulk TR8 x4 stages copy+colsum");
+            run(k_tma<12, 3, true>, 12, 3, "TMA-bulk TR12 x3 stages copy+colsum");
+            run(k_tma<16, 2, true>, 16, 2, "TMA-bulk TR16 x2 stages copy+colsum");
         }
         cudaFree(a); cudaFree(o); cudaFree(cs); cudaFree(ctr);
     }
