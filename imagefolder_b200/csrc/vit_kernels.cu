@@ -367,9 +367,21 @@ __device__ __forceinline__ float erf_as(float z) {
     p = p * p; p = p * p; p = p * p; p = p * p;          // ^16 (overflows to +inf for |z| > ~9 -> erf = 1, as it should)
     return copysignf(1.0f - rcp_fast(p), z);
 }
+// gelu(x) = x/2 * (1 + erf(x/sqrt2)) with erf(|z|) = 1 - r, r = (1 + a1|z| + ... + a6|z|^6)^-16 (A&S 7.1.28):
+//   gelu(x) = h + |h| * (1 - r) = (h + |h|) - |h| * r ,  h = x/2.
+// The 1/sqrt2 of z is folded into the coefficients (b_k = a_k * 2^(-k/2)) and the sign handling into the abs/neg operand
+// modifiers, which takes 3 instructions off the previous form (the kernel is instruction-issue bound, not HBM bound).
 __device__ __forceinline__ float gelu_f(float x) {
+    const float a = fabsf(x);
+    float p = fmaf(a, 5.382975000e-06f, 4.889063564e-05f);
+    p = fmaf(p, a, 3.800357500e-05f);
+    p = fmaf(p, a, 3.277626324e-03f);
+    p = fmaf(p, a, 2.114100615e-02f);
+    p = fmaf(p, a, 4.986734697e-02f);
+    p = fmaf(p, a, 1.0f);
+    p = p * p; p = p * p; p = p * p; p = p * p;
     const float h = 0.5f * x;
-    return fmaf(h, erf_as(x * 0.70710678118654752f), h);
+    return fmaf(-fabsf(h), rcp_fast(p), h + fabsf(h));
 }
 __device__ __forceinline__ float dgelu_f(float x) {
     const float e = ex2_fast(x * x * -0.72134752044448170f);      // exp(-x^2 / 2)
@@ -462,44 +474,101 @@ __global__ void gelu_bwd_kernel(const uint4 *__restrict__ x, const float *__rest
 // dq, dk, dv: each [M, C] bf16 dense (what the SDPA backward returns for q/k/v views of a packed
 // [M, 3C] projection) -> dqkv [M, 3C], and (optionally) g_bias [3C] = column sums of dqkv = the gradient of the
 // qkv projection bias, which autograd would otherwise compute with one more full pass over dqkv.
-// A thread owns one 16-byte column chunk of the packed row and walks rows with a grid stride, PACK_RU rows in flight.
-constexpr int PACK_RU = 4;
-__global__ void pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__restrict__ dk, const uint4 *__restrict__ dv,
-                                uint4 *__restrict__ out, float *__restrict__ g_bias, int M, int C8) {
-    const int per_row = 3 * C8, step = gridDim.x * PACK_RU;
-    for (int c = threadIdx.x; c < per_row; c += blockDim.x) {
-        const int which = c / C8, cc = c - which * C8;
-        const uint4 *src = which == 0 ? dq : (which == 1 ? dk : dv);
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uint4 v[PACK_RU], vn[PACK_RU];
-        int row0 = blockIdx.x * PACK_RU;
+// Same TMA-bulk staged skeleton as residual_ln_bwd_kernel: warp 0 stages PACK_TR rows of the three sources per tile,
+// consumer warp w copies row w (a lane owns 16-byte column chunks j*32 + lane of the PACKED row) and keeps the column
+// sums in registers; one atomicAdd per column per CTA at the end (g_bias zeroed by the launcher).
+constexpr int PACK_TR = 8;
+constexpr int PACK_NST = 4;
+constexpr int PACK_NCH = 12;                 // 16-byte chunks per lane: 3*C/8 <= 384  (C <= 1024)
+constexpr int PACK_THREADS = (PACK_TR + 1) * 32;
+__global__ void __launch_bounds__(PACK_THREADS, 1)
+pack_qkv_kernel(const uint4 *__restrict__ dq, const uint4 *__restrict__ dk, const uint4 *__restrict__ dv,
+                uint4 *__restrict__ out, float *__restrict__ g_bias, int *__restrict__ counter, int M, int C8) {
+    constexpr int TR = PACK_TR, NST = PACK_NST;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[NST], empty[NST];
+    __shared__ int tile_of[NST];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (M + TR - 1) / TR, per_row = 3 * C8;
+    const uint32_t src_row = (uint32_t)C8 * 16;                    // bytes of one source row
+    const size_t stage_bytes = (size_t)3 * TR * src_row;           // [3][TR][C8] uint4
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TR); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0;; ++it) {
+                const int st = it % NST;
+                mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                const int tile = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(counter, 1);
+                tile_of[st] = tile;
+                if (tile >= ntiles) { mbar_arrive(&full[st]); break; }
+                const int r0 = tile * TR, nr = min(TR, M - r0);
+                unsigned char *dst = smem + st * stage_bytes;
+                mbar_expect_tx(&full[st], 3u * nr * src_row);
+                bulk_g2s(dst, dq + (size_t)r0 * C8, nr * src_row, &full[st]);
+                bulk_g2s(dst + (size_t)TR * src_row, dk + (size_t)r0 * C8, nr * src_row, &full[st]);
+                bulk_g2s(dst + (size_t)2 * TR * src_row, dv + (size_t)r0 * C8, nr * src_row, &full[st]);
+            }
+        }
+    } else {
+        const int cw = warp - 1;
+        float acc[PACK_NCH][8];
 #pragma unroll
-        for (int u = 0; u < PACK_RU; ++u)
-            if (row0 + u < M) v[u] = src[(size_t)(row0 + u) * C8 + cc];
-        for (; row0 < M; row0 += step) {            // software-pipelined like gelu_bwd_kernel
-            const int nxt = row0 + step;
+        for (int j = 0; j < PACK_NCH; ++j)
 #pragma unroll
-            for (int u = 0; u < PACK_RU; ++u)
-                if (nxt + u < M) vn[u] = src[(size_t)(nxt + u) * C8 + cc];
+            for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+        for (int it = 0;; ++it) {
+            const int st = it % NST;
+            mbar_wait(&full[st], (it / NST) & 1);
+            const int tile = tile_of[st];
+            if (tile >= ntiles) break;
+            const int row = tile * TR + cw;
+            if (row < M) {
+                const unsigned char *base = smem + st * stage_bytes + (size_t)cw * src_row;
 #pragma unroll
-            for (int u = 0; u < PACK_RU; ++u) {
-                if (row0 + u >= M) continue;
-                out[(size_t)(row0 + u) * per_row + c] = v[u];
-                if (g_bias) {
-                    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v[u]);
+                for (int j = 0; j < PACK_NCH; ++j) {
+                    const int c = j * 32 + lane;
+                    if (c < per_row) {
+                        const int which = c / C8, cc = c - which * C8;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(base + (size_t)which * TR * src_row + (size_t)cc * 16);
+                        out[(size_t)row * per_row + c] = v;
+                        if (g_bias) {
+                            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&v);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float2 f = __bfloat1622float2(p[k]);
-                        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+                            for (int k = 0; k < 4; ++k) {
+                                float2 f = __bfloat1622float2(p[k]);
+                                acc[j][2 * k] += f.x; acc[j][2 * k + 1] += f.y;
+                            }
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < PACK_RU; ++u) v[u] = vn[u];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
         }
         if (g_bias) {
+            asm volatile("bar.sync 1, %0;" ::"n"(PACK_TR * 32) : "memory");   // every consumer is past its last tile
+            float *red = reinterpret_cast<float *>(smem) + (size_t)cw * per_row * 8;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(g_bias + c * 8 + k, acc[k]);
+            for (int j = 0; j < PACK_NCH; ++j) {
+                const int c = j * 32 + lane;
+                if (c < per_row)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) red[c * 8 + k] = acc[j][k];
+            }
+        }
+    }
+    if (g_bias) {
+        __syncthreads();
+        const float *red = reinterpret_cast<const float *>(smem);
+        for (int e = threadIdx.x; e < per_row * 8; e += blockDim.x) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < TR; ++w) t += red[(size_t)w * per_row * 8 + e];
+            atomicAdd(g_bias + e, t);
         }
     }
 }
@@ -604,18 +673,28 @@ int xq_vit_residual_ln_bwd(const float *g_xout, const void *g_y, const float *x_
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 
+size_t xq_vit_pack_workspace_bytes(void) { return 256; }
+
 int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, float *g_bias, size_t M, int C,
-                    void *stream) {
-    if (!dq || !dk || !dv || !dqkv || M == 0 || M > 0x7fffffffu || C <= 0 || (C & 7)) return XQ_ERR_ARG;
+                    void *workspace, size_t workspace_bytes, void *stream) {
+    if (!dq || !dk || !dv || !dqkv || M == 0 || M > 0x7fffffffu || C <= 0 || (C & 7) || !workspace) return XQ_ERR_ARG;
+    if (workspace_bytes < 256) return XQ_ERR_WORKSPACE;
+    if (3 * (C / 8) > PACK_NCH * 32) return XQ_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int C8 = C / 8, per_row = 3 * C8;
-    const int threads = per_row >= 288 ? 288 : (per_row >= 192 ? 192 : 96);
-    const int rows4 = (int)((M + PACK_RU - 1) / PACK_RU);
-    int grid = persistent_grid(pack_qkv_kernel, threads);
-    if (rows4 < grid) grid = rows4;
+    const int C8 = C / 8;
+    int *counter = (int *)workspace;     // dynamic tile counter, reset on the stream before each launch
+    if (cudaMemsetAsync(counter, 0, sizeof(int), st) != cudaSuccess) return XQ_ERR_CUDA;
     if (g_bias && cudaMemsetAsync(g_bias, 0, sizeof(float) * 3 * (size_t)C, st) != cudaSuccess) return XQ_ERR_CUDA;
-    pack_qkv_kernel<<<grid, threads, 0, st>>>((const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv, (uint4 *)dqkv,
-                                              g_bias, (int)M, C8);
+    const int ntiles = (int)((M + PACK_TR - 1) / PACK_TR);
+    int grid = bwd_grid();
+    if (grid > ntiles) grid = ntiles;
+    size_t smem = (size_t)PACK_NST * 3 * PACK_TR * C8 * 16;
+    const size_t red = sizeof(float) * (size_t)PACK_TR * 3 * C8 * 8;
+    if (smem < red) smem = red;
+    if (cudaFuncSetAttribute(pack_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return XQ_ERR_CUDA;
+    pack_qkv_kernel<<<grid, PACK_THREADS, smem, st>>>((const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv,
+                                                      (uint4 *)dqkv, g_bias, counter, (int)M, C8);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 

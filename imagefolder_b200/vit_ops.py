@@ -145,8 +145,10 @@ def _sdpa_packed_backward(inner, dims, g, want_bias_grad: bool):
         if want_bias_grad:
             db = torch.empty(3 * C, dtype=torch.float32, device=dq.device)
         L = _lib()
+        ws = torch.empty(int(L.xq_vit_pack_workspace_bytes()), dtype=torch.uint8, device=dq.device)
         _call("xq_vit_pack_qkv", 1, L.xq_vit_pack_qkv, _ptr(flat[0]), _ptr(flat[1]), _ptr(flat[2]), _ptr(dqkv),
-              _ptr(db) if db is not None else None, B * N, C, _stream(dq.device), nbytes=B * N * C * 12)
+              _ptr(db) if db is not None else None, B * N, C, _ptr(ws), ws.numel(), _stream(dq.device),
+              nbytes=B * N * C * 12)
     else:  # layout the library did not produce in our runs; keep correctness
         torch.stack([t.reshape(B, N, C) for t in flat], dim=2, out=dqkv.view(B, N, 3, C))
         if want_bias_grad:

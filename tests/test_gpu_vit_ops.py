@@ -173,20 +173,21 @@ def test_pack_qkv_cabi_ragged_rows_and_bias():
     from imagefolder_b200 import _capi
     L = _capi.lib()
     torch.manual_seed(6)
-    for M, C in [(1, 8), (7, 64), (1031, 768), (4099, 384)]:
+    for M, C in [(1, 8), (7, 64), (1031, 768), (4099, 384), (2500, 1024)]:
         dq, dk, dv = (torch.randn(M, C, device="cuda").to(torch.bfloat16) for _ in range(3))
         out = torch.empty(M, 3 * C, device="cuda", dtype=torch.bfloat16)
         gb = torch.full((3 * C,), 7.0, device="cuda")
+        ws = torch.empty(int(L.xq_vit_pack_workspace_bytes()), dtype=torch.uint8, device="cuda")
         _capi.check(L.xq_vit_pack_qkv(_capi.ptr(dq), _capi.ptr(dk), _capi.ptr(dv), _capi.ptr(out), _capi.ptr(gb), M, C,
-                                      _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
+                                      _capi.ptr(ws), ws.numel(), _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
         ref = torch.cat([dq, dk, dv], dim=1)
         assert torch.equal(out, ref)
         np.testing.assert_allclose(gb.cpu().numpy(), ref.float().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
         out.zero_()
         _capi.check(L.xq_vit_pack_qkv(_capi.ptr(dq), _capi.ptr(dk), _capi.ptr(dv), _capi.ptr(out), None, M, C,
-                                      _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
+                                      _capi.ptr(ws), ws.numel(), _capi.stream_ptr(out.device)), "xq_vit_pack_qkv")
         assert torch.equal(out, ref)
-    assert L.xq_vit_pack_qkv(None, None, None, None, None, 4, 8, None) != 0
+    assert L.xq_vit_pack_qkv(None, None, None, None, None, 4, 8, None, 0, None) != 0
 
 
 def test_patch_embed_gemm_matches_conv():
