@@ -260,9 +260,10 @@ def run_ours(a):
         gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
         tfs = flops_alg / (kern_ms * 1e-3) / 1e12
         tc = (C in (32, 64)) and os.environ.get("XQ_VQ_ALGO", "auto")[0] != "e"
-        # TMEM -> register read floor of the tcgen05 path: every approximate score (N*V fp32) crosses the 64 B/clk/SM
-        # tcgen05.ld port once (B300_MICROARCH.md "LDTM throughput"; confirmed by the in-kernel clock trace)
-        tmem_floor_ms = rows * V * 4 / (64.0 * 148 * 1.9e9) * 1e3
+        # TMEM -> register read floor of the tcgen05 path: every approximate score (N*V fp32) crosses the tcgen05.ld
+        # port once.  Measured in-kernel (tools/vq_tc_trace.py): 2 co-resident CTAs each drain a 64 KB tile per ~1.05 k clk
+        # = ~125 B/clk per SM, unchanged with 4 or 8 epilogue warps per CTA (B300_MICROARCH.md quotes 64 B/cyc per reader)
+        tmem_floor_ms = rows * V * 4 / (125.0 * 148 * 1.9e9) * 1e3
         roof = {"bound": "tensor", "kernel": ("vq_search_tc_kernel (tcgen05 TF32 screening + exact fp32 rescoring)" if tc
                                                else "vq_search_kernel (exact fp32 CUDA-core)") +
                           "; timed = the xq_vq_forward call (codebook prep + search + loss finalize)",
