@@ -105,6 +105,16 @@ def lib() -> ctypes.CDLL:
     L.xq_vit_gelu_fwd.argtypes = [vp, f32p, vp, c_int, c_int, vp]
     L.xq_vit_gelu_bwd.restype = c_int
     L.xq_vit_gelu_bwd.argtypes = [vp, f32p, vp, vp, f32p, c_int, c_int, vp]
+    L.xq_lpips_workspace_bytes.restype = c_size_t
+    L.xq_lpips_workspace_bytes.argtypes = [c_int, c_int]
+    L.xq_lpips_layer_forward.restype = c_int
+    L.xq_lpips_layer_forward.argtypes = [vp, vp, c_int, f32p, c_int, c_int, c_int, c_float, c_int, f32p, vp, c_size_t, vp]
+    L.xq_lpips_layer_backward.restype = c_int
+    L.xq_lpips_layer_backward.argtypes = [vp, vp, c_int, f32p, c_int, c_int, c_int, c_float, f32p, vp, vp]
+    L.xq_diffaug_forward.restype = c_int
+    L.xq_diffaug_forward.argtypes = [f32p, f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, f32p, f32p, vp]
+    L.xq_diffaug_backward.restype = c_int
+    L.xq_diffaug_backward.argtypes = [f32p, f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, f32p, f32p, vp]
     _lib = L
     return L
 
@@ -184,4 +194,6 @@ EXPORTED_SYMBOLS = [
     "xq_ms_workspace_bytes", "xq_ms_saved_bytes", "xq_ms_total_tokens", "xq_ms_forward", "xq_ms_backward",
     "xq_ms_decode", "xq_ms_embed", "xq_usage_ema", "xq_vit_residual_ln_fwd", "xq_vit_ln_bwd_workspace_bytes",
     "xq_vit_residual_ln_bwd", "xq_vit_gelu_fwd", "xq_vit_gelu_bwd", "xq_vit_pack_qkv", "xq_vit_pack_workspace_bytes", "xq_vit_patchify",
+    "xq_lpips_workspace_bytes", "xq_lpips_layer_forward", "xq_lpips_layer_backward", "xq_diffaug_forward",
+    "xq_diffaug_backward",
 ]

@@ -225,6 +225,32 @@ int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, voi
 int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *g_bias, int M, int C,
                     void *stream);
 
+/*
+ * ---- loss stack -------------------------------------------------------------------
+ * LPIPS stage distance (tokenizer/tokenizer_image/lpips.py:79-90): for one VGG stage with feature maps f0, f1
+ * [B,C,H*W] (fp32, or bf16 when is_bf16) and the stage's `lin` weights lin_w [C]:
+ *   out[b] (+)= mean_p sum_c lin_w[c] * ( f0/(|f0|_c + eps) - f1/(|f1|_c + eps) )^2      (accumulate != 0: add to out)
+ * backward returns the gradient w.r.t. f1 (swap the maps for f0); g_out [B] is d loss / d out.
+ * The fp64 per-CTA partials live in the caller's workspace (xq_lpips_workspace_bytes).
+ */
+size_t xq_lpips_workspace_bytes(int B, int HW);
+int xq_lpips_layer_forward(const void *f0, const void *f1, int is_bf16, const float *lin_w, int B, int C, int HW, float eps,
+                           int accumulate, float *out, void *workspace, size_t workspace_bytes, void *stream);
+int xq_lpips_layer_backward(const void *f0, const void *f1, int is_bf16, const float *lin_w, int B, int C, int HW, float eps,
+                            const float *g_out, void *g_f1, void *stream);
+/*
+ * DiffAug.aug without the warm-up blur (tokenizer/tokenizer_image/diffaug.py:60-118): translation (zero fill), colour
+ * (brightness, saturation about the per-pixel channel mean, contrast about the per-sample mean) and cutout.
+ *   x, y, g, gx  [B,C,H,W] fp32, C <= 8 ;  rand01 [7,B] = the reference's torch.rand(7,B,1,1) (:64) ;
+ *   flags: bit0 translation, bit1 colour, bit2 cutout (the reference's three `torch.rand(3) <= prob` draws, :61) ;
+ *   cut_h, cut_w = round(H*cutout), round(W*cutout) ; sums [B] scratch.
+ * backward is the exact transpose of the (per-sample affine) forward map.
+ */
+int xq_diffaug_forward(const float *x, const float *rand01, int B, int C, int H, int W, int flags, int cut_h, int cut_w,
+                       float *y, float *sums, void *stream);
+int xq_diffaug_backward(const float *g, const float *rand01, int B, int C, int H, int W, int flags, int cut_h, int cut_w,
+                        float *gx, float *sums, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -211,7 +211,127 @@ def case_var_helpers(Q, name, C, B, patch_nums, seed=11, share=4, **qkw):
     print(name, "fhat abs max", float(fh_last.abs().max()))
 
 
+def import_loss_reference():
+    """row f-1: the reference's loss stack.  wandb is absent here and the LPIPS / DINO checkpoints cannot be downloaded:
+    wandb is stubbed, and only code paths that need no pretrained weights are run."""
+    sys.path.insert(0, REF)
+    for m in ["wandb", "timm", "timm.models", "timm.layers", "peft", "webdataset"]:
+        sys.modules.setdefault(m, _Stub(m))
+    if not tdist.is_initialized():
+        tdist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    from tokenizer.tokenizer_image import diffaug, lpips, vq_loss, discriminator_dino
+    return diffaug, lpips, vq_loss, discriminator_dino
+
+
+def case_loss_stack():
+    diffaug, lpips, vq_loss, ddino = import_loss_reference()
+    d = {}
+    # ---- DiffAug.aug (diffaug.py:45-118) for every flag combination that the three Bernoulli draws can produce;
+    # the CPU generator decides the flags (torch.rand(3) <= prob) and the parameters (torch.rand(7,B,1,1))
+    cases = []
+    for ci, (seed, prob, B, C, H, W) in enumerate([(0, 1.0, 3, 3, 32, 32), (1, 1.0, 2, 3, 40, 24), (2, 0.5, 4, 3, 16, 16),
+                                                   (5, 0.5, 2, 3, 20, 20), (7, 0.34, 3, 3, 16, 16), (9, 0.0, 2, 3, 8, 8),
+                                                   (11, 0.6, 2, 1, 12, 12), (13, 0.5, 2, 3, 16, 16), (0, 0.5, 3, 3, 24, 24),
+                                                   (1, 0.5, 2, 3, 16, 20), (4, 0.5, 3, 3, 10, 10), (16, 0.5, 2, 3, 16, 16),
+                                                   (4, 0.5, 2, 3, 5, 5)]):
+        aug = diffaug.DiffAug(prob=prob, cutout=0.2)
+        torch.manual_seed(100 + seed)
+        x = torch.randn(B, C, H, W, requires_grad=True)
+        torch.manual_seed(seed)                 # the draws of aug() start here
+        y = aug.aug(x, 0)
+        g = torch.randn_like(y)
+        if y.requires_grad:
+            (gx,) = torch.autograd.grad(y, x, g)
+        else:
+            gx = g.clone()
+        # replay the generator to record what was drawn
+        torch.manual_seed(seed)
+        flags3 = (torch.rand(3) <= abs(prob)) if abs(prob) >= 1e-6 else torch.zeros(3, dtype=torch.bool)
+        rand01 = torch.rand(7, B, 1, 1) if bool(flags3.any()) else torch.zeros(7, B, 1, 1)
+        d[f"aug{ci}_x"], d[f"aug{ci}_y"], d[f"aug{ci}_g"], d[f"aug{ci}_gx"] = npy(x), npy(y), npy(g), npy(gx)
+        d[f"aug{ci}_flags"] = npy(flags3).astype(np.int64)
+        d[f"aug{ci}_rand01"] = npy(rand01).reshape(7, B)
+        d[f"aug{ci}_meta"] = np.array([seed, B, C, H, W], dtype=np.int64)
+        d[f"aug{ci}_prob"] = np.float64(prob)
+        cases.append(ci)
+    d["aug_cases"] = np.array(cases)
+    # ---- LPIPS stage arithmetic (lpips.py:79-90, 152-159) on synthetic post-ReLU features with the reference's functions
+    torch.manual_seed(3)
+    for li, (B, C, H, W) in enumerate([(2, 64, 8, 8), (3, 128, 5, 7), (2, 512, 3, 3)]):
+        f0 = torch.relu(torch.randn(B, C, H, W))
+        f1 = (f0 + 0.3 * torch.randn(B, C, H, W)).relu().requires_grad_(True)
+        lin = lpips.NetLinLayer(C, use_dropout=True).eval()
+        lin.model[1].weight.data.uniform_(0, 0.2)
+        diff = (lpips.normalize_tensor(f0) - lpips.normalize_tensor(f1)) ** 2
+        val = lpips.spatial_average(lin.model(diff), keepdim=True)
+        g = torch.randn_like(val)
+        (gf1,) = torch.autograd.grad(val, f1, g)
+        d[f"lp{li}_f0"], d[f"lp{li}_f1"], d[f"lp{li}_w"] = npy(f0), npy(f1), npy(lin.model[1].weight).reshape(-1)
+        d[f"lp{li}_val"], d[f"lp{li}_g"], d[f"lp{li}_gf1"] = npy(val).reshape(-1), npy(g).reshape(-1), npy(gf1)
+    sl = lpips.ScalingLayer()
+    xin = torch.rand(2, 3, 4, 4) * 2 - 1
+    d["scal_x"], d["scal_y"] = npy(xin), npy(sl(xin))
+    # state-dict key names of the reference LPIPS (built without downloads: torchvision weights / ckpt loading patched out)
+    import torchvision
+    orig_vgg = torchvision.models.vgg16
+    lpips.models.vgg16 = lambda pretrained=False, **k: orig_vgg(weights=None)
+    lpips.LPIPS.load_from_pretrained = lambda self, name="vgg_lpips": None
+    ref_lp = lpips.LPIPS().eval()
+    d["lpips_keys"] = np.array(sorted(ref_lp.state_dict().keys()))
+    d["lpips_shapes"] = np.array([str(tuple(v.shape)) for k, v in sorted(ref_lp.state_dict().items())])
+    # ---- GAN loss functions and schedules (vq_loss.py:18-77)
+    torch.manual_seed(4)
+    lr, lf = torch.randn(5, 7) * 2, torch.randn(5, 7) * 2
+    d["gan_lr"], d["gan_lf"] = npy(lr), npy(lf)
+    d["hinge_d"] = npy(vq_loss.hinge_d_loss(lr, lf))
+    d["vanilla_d"] = npy(vq_loss.vanilla_d_loss(lr, lf))
+    d["nonsat_d"] = npy(vq_loss.non_saturating_d_loss(lr, lf))
+    d["hinge_g"] = npy(vq_loss.hinge_gen_loss(lf))
+    d["nonsat_g"] = npy(vq_loss.non_saturating_gen_loss(lf))
+    ema = vq_loss.LeCAM_EMA()
+    ema.update(lr, lf)
+    ema.update(lr * 0.5, lf + 1)
+    d["lecam_ema"] = np.array([ema.logits_real_ema, ema.logits_fake_ema])
+    d["lecam_reg"] = npy(vq_loss.lecam_reg(lr, lf, ema))
+    d["adopt"] = np.array([vq_loss.adopt_weight(0.5, s, threshold=10, value=0.0) for s in (0, 9, 10, 11)])
+    d["anneal"] = np.array([vq_loss.anneal_weight(1.0, s, threshold=10, initial_value=0.3, final_value=0.1, anneal_steps=20)
+                            for s in (0, 10, 15, 30, 31, 100)])
+    # ---- DinoDisc pieces that need no checkpoint: BatchNormLocal, one head, the frozen ViT with random weights
+    torch.manual_seed(6)
+    bn = ddino.BatchNormLocal(6, virtual_bs=4)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    xb = torch.randn(8, 6, 9)
+    d["bnl_x"], d["bnl_w"], d["bnl_b"], d["bnl_y"] = npy(xb), npy(bn.weight), npy(bn.bias), npy(bn(xb))
+    vit = ddino.FrozenDINOSmallNoDrop(depth=3, key_depths=(0, 2), embed_dim=48, num_heads=3)
+    for p_ in vit.parameters():
+        p_.data.normal_(0, 0.05)
+    img = torch.rand(2, 3, 224, 224) * 2 - 1
+    acts = vit(img)
+    d["dino_keys"] = np.array(sorted(vit.state_dict().keys()))
+    for k, v in vit.state_dict().items():
+        d["dinow_" + k] = npy(v)
+    d["dino_img"] = npy(img)[:, :, ::8, ::8].copy()       # the test rebuilds the image by nearest upsampling x8
+    img_up = torch.from_numpy(d["dino_img"]).repeat_interleave(8, 2).repeat_interleave(8, 3)
+    acts = vit(img_up)
+    for i, a in enumerate(acts):
+        d[f"dino_act{i}"] = npy(a)
+    head = torch.nn.Sequential(
+        ddino.make_block(48, kernel_size=1, norm_type="bn", norm_eps=1e-6, using_spec_norm=True),
+        ddino.ResidualBlock(ddino.make_block(48, kernel_size=9, norm_type="bn", norm_eps=1e-6, using_spec_norm=True)),
+        ddino.SpectralConv1d(48, 1, kernel_size=1, padding=0)).eval()
+    d["head_keys"] = np.array(sorted(head.state_dict().keys()))
+    for k, v in head.state_dict().items():
+        d["headw_" + k] = npy(v)
+    d["head_y"] = npy(head(acts[0]))
+    np.savez_compressed(os.path.join(OUT, "loss_stack.npz"), **d)
+    print("loss_stack: aug cases", len(cases), "lpips keys", len(d["lpips_keys"]), "dino acts", len(acts))
+
+
 def main():
+    if "--loss-only" in sys.argv:
+        case_loss_stack()
+        return
     VQ, VQ2, LFQ, add_perturbation = import_reference()
     if "--var-helpers-only" in sys.argv:
         case_var_helpers(VQ2, "varhelp_msvr", 16, 3, [1, 1, 2, 3, 3, 4, 5, 6, 8, 11], args=(256, 16))
@@ -236,6 +356,7 @@ def main():
     case_var_helpers(VQ2, "varhelp_msvr", 16, 3, [1, 1, 2, 3, 3, 4, 5, 6, 8, 11], args=(256, 16))
     case_var_helpers(VQ2, "varhelp_shared1", 8, 2, [1, 2, 4, 7], share=1, args=(128, 8), seed=12)
     case_var_helpers(LFQ, "varhelp_lfq", 10, 2, [1, 2, 3, 5], args=(2 ** 10, 10), seed=13)
+    case_loss_stack()
 
 
 def case_cnn(name="cnn_small", seed=5):
