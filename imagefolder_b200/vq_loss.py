@@ -1,0 +1,212 @@
+"""Tokenizer training loss (reconstruction + LPIPS + adversarial + codebook terms) -- tokenizer/tokenizer_image/vq_loss.py.
+
+`VQLoss` keeps the reference's constructor, its `forward(codebook_loss, sem_loss, detail_loss, dependency_loss, inputs,
+reconstructions, optimizer_idx, global_step, last_layer, logger, log_every, fade_blur_schedule)` call (:150-152) and its
+sub-module names (`discriminator`, `perceptual_loss`: checkpoint keys).  The HBM-bound pieces under it run as fused CUDA
+kernels: the LPIPS stage distances (lpips.py) and DiffAug (diffaug.py); the VGG16 / DINO ViT-S trunks are library kernels.
+Differences, all host-side: wandb and a process group are optional (the reference needs both even on one GPU, :143-144),
+and the LeCAM running means stay on the device (the reference `.item()`s two scalars per discriminator step, :68-69).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .diffaug import DiffAug
+from .discriminator_dino import DinoDisc as DINODiscriminator
+from .lpips import LPIPS
+
+
+# ---- GAN objectives (vq_loss.py:18-45) -------------------------------------------------------------------------------
+def hinge_d_loss(logits_real, logits_fake):
+    return 0.5 * (torch.mean(F.relu(1. - logits_real)) + torch.mean(F.relu(1. + logits_fake)))
+
+
+def vanilla_d_loss(logits_real, logits_fake):
+    return 0.5 * (torch.mean(F.softplus(-logits_real)) + torch.mean(F.softplus(logits_fake)))
+
+
+def non_saturating_d_loss(logits_real, logits_fake):
+    # argument order as in the reference (:33-34): the constant tensor is the *input*, the logits are the *target*
+    real = torch.mean(F.binary_cross_entropy_with_logits(torch.ones_like(logits_real), logits_real))
+    fake = torch.mean(F.binary_cross_entropy_with_logits(torch.zeros_like(logits_fake), logits_fake))
+    return 0.5 * (real + fake)
+
+
+def hinge_gen_loss(logit_fake):
+    return -torch.mean(logit_fake)
+
+
+def non_saturating_gen_loss(logit_fake):
+    return torch.mean(F.binary_cross_entropy_with_logits(torch.ones_like(logit_fake), logit_fake))
+
+
+def adopt_weight(weight, global_step, threshold=0, value=0.):
+    return value if global_step < threshold else weight
+
+
+def anneal_weight(weight, global_step, threshold=0, initial_value=0.3, final_value=0.1, anneal_steps=2000):
+    if global_step < threshold:
+        return initial_value
+    if global_step < threshold + anneal_steps:
+        return initial_value - (global_step - threshold) / anneal_steps * (initial_value - final_value)
+    return final_value
+
+
+class LeCAM_EMA(object):
+    """running means of the real / fake logits (:64-73); kept as 0-dim tensors on the logits' device (no host sync)."""
+
+    def __init__(self, init=0., decay=0.999):
+        self.logits_real_ema = init
+        self.logits_fake_ema = init
+        self.decay = decay
+
+    def update(self, logits_real, logits_fake):
+        self.logits_real_ema = self.logits_real_ema * self.decay + logits_real.detach().float().mean() * (1 - self.decay)
+        self.logits_fake_ema = self.logits_fake_ema * self.decay + logits_fake.detach().float().mean() * (1 - self.decay)
+
+
+def lecam_reg(real_pred, fake_pred, lecam_ema):
+    return torch.mean(F.relu(real_pred - lecam_ema.logits_fake_ema).pow(2)) + \
+        torch.mean(F.relu(lecam_ema.logits_real_ema - fake_pred).pow(2))
+
+
+class PatchGANDiscriminator(nn.Module):
+    """pix2pix N-layer PatchGAN (discriminator_patchgan.py:6-63; BatchNorm variant), keys `main.{i}.*`."""
+
+    def __init__(self, input_nc=3, ndf=64, n_layers=3, use_actnorm=False):
+        super().__init__()
+        if use_actnorm:
+            raise NotImplementedError("ActNorm variant of the PatchGAN discriminator is not selected by any shipped config")
+        seq = [nn.Conv2d(input_nc, ndf, 4, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        mult = 1
+        for n in range(1, n_layers + 1):
+            prev, mult = mult, min(2 ** n, 8)
+            seq += [nn.Conv2d(ndf * prev, ndf * mult, 4, stride=2 if n < n_layers else 1, padding=1, bias=False),
+                    nn.BatchNorm2d(ndf * mult), nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(ndf * mult, 1, 4, stride=1, padding=1)]
+        self.main = nn.Sequential(*seq)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight.data, 0.0, 0.02)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.normal_(m.weight.data, 1.0, 0.02)
+                nn.init.constant_(m.bias.data, 0)
+
+    def forward(self, input):
+        return self.main(input)
+
+
+class VQLoss(nn.Module):
+    def __init__(self, disc_start, disc_loss="hinge", disc_dim=64, disc_type='patchgan', image_size=256,
+                 disc_num_layers=3, disc_in_channels=3, disc_weight=1.0, disc_adaptive_weight=False,
+                 gen_adv_loss='hinge', reconstruction_loss='l2', reconstruction_weight=1.0,
+                 codebook_weight=1.0, perceptual_weight=1.0, lecam_loss_weight=None, norm_type='bn', aug_prob=1,
+                 ):
+        super().__init__()
+        assert disc_type in ["patchgan", "stylegan", 'dinodisc', 'samdisc']
+        assert disc_loss in ["hinge", "vanilla", "non-saturating"]
+        assert gen_adv_loss in ["hinge", "non-saturating"]
+        self.disc_type = disc_type
+        if disc_type == "patchgan":
+            self.discriminator = PatchGANDiscriminator(input_nc=disc_in_channels, n_layers=disc_num_layers, ndf=disc_dim)
+        elif disc_type == "dinodisc":
+            self.discriminator = DINODiscriminator(norm_type=norm_type)
+            self.daug = DiffAug(prob=aug_prob, cutout=0.2)
+        else:
+            raise NotImplementedError(f"disc_type={disc_type!r}: no shipped config selects it (all use 'dinodisc'); not built")
+        self.disc_loss = {"hinge": hinge_d_loss, "vanilla": vanilla_d_loss, "non-saturating": non_saturating_d_loss}[disc_loss]
+        self.discriminator_iter_start = disc_start
+        self.disc_weight = disc_weight
+        self.disc_adaptive_weight = disc_adaptive_weight
+        self.gen_adv_loss = {"hinge": hinge_gen_loss, "non-saturating": non_saturating_gen_loss}[gen_adv_loss]
+        self.perceptual_loss = LPIPS().eval()
+        self.perceptual_weight = perceptual_weight
+        if reconstruction_loss not in ("l1", "l2"):
+            raise ValueError(f"Unknown rec loss '{reconstruction_loss}'.")
+        self.rec_loss = F.l1_loss if reconstruction_loss == "l1" else F.mse_loss
+        self.rec_weight = reconstruction_weight
+        self.codebook_weight = codebook_weight
+        self.lecam_loss_weight = lecam_loss_weight
+        if self.lecam_loss_weight is not None:
+            self.lecam_ema = LeCAM_EMA()
+        self.wandb_tracker = None
+        try:                                            # optional experiment tracking (the reference requires it)
+            import torch.distributed as tdist
+            if (not tdist.is_initialized()) or tdist.get_rank() == 0:
+                import wandb
+                self.wandb_tracker = wandb.init(project='MSVQ')
+        except Exception:
+            self.wandb_tracker = None
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.perceptual_loss.eval()                     # LPIPS is frozen and always in eval mode (:128)
+        return self
+
+    def calculate_adaptive_weight(self, nll_loss, g_loss, last_layer):
+        nll_grads = torch.autograd.grad(nll_loss, last_layer, retain_graph=True)[0]
+        g_grads = torch.autograd.grad(g_loss, last_layer, retain_graph=True)[0]
+        d_weight = torch.norm(nll_grads) / (torch.norm(g_grads) + 1e-4)
+        return torch.clamp(d_weight, 0.0, 1e4).detach()
+
+    def _disc_in(self, x, fade_blur_schedule):
+        if self.disc_type != "dinodisc":
+            return x
+        return self.daug.aug(x, 0 if fade_blur_schedule < 1e-6 else fade_blur_schedule)
+
+    def forward(self, codebook_loss, sem_loss, detail_loss, dependency_loss, inputs, reconstructions, optimizer_idx,
+                global_step, last_layer=None, logger=None, log_every=100, fade_blur_schedule=0):
+        disc_weight = adopt_weight(self.disc_weight, global_step, threshold=self.discriminator_iter_start)
+        log_now = logger is not None and global_step % log_every == 0
+        if optimizer_idx == 0:                          # ---- generator update (:153-207)
+            rec_loss = self.rec_loss(inputs.contiguous(), reconstructions.contiguous())
+            p_loss = torch.mean(self.perceptual_loss(inputs.contiguous(), reconstructions.contiguous()))
+            logits_fake = self.discriminator(self._disc_in(reconstructions.contiguous(), fade_blur_schedule))
+            generator_adv_loss = self.gen_adv_loss(logits_fake)
+            if self.disc_adaptive_weight:
+                null_loss = self.rec_weight * rec_loss + self.perceptual_weight * p_loss
+                adaptive = self.calculate_adaptive_weight(null_loss, generator_adv_loss, last_layer=last_layer)
+            else:
+                adaptive = 1
+            sem_loss = 0 if sem_loss is None else sem_loss
+            detail_loss = 0 if detail_loss is None else detail_loss
+            dependency_loss = 0 if dependency_loss is None else dependency_loss
+            loss = self.rec_weight * rec_loss + self.perceptual_weight * p_loss + \
+                adaptive * disc_weight * generator_adv_loss + \
+                codebook_loss[0] + codebook_loss[1] + codebook_loss[2] + sem_loss + detail_loss + dependency_loss
+            if log_now or (self.wandb_tracker is not None and global_step % log_every == 0):
+                stats = {"rec_loss": self.rec_weight * rec_loss, "perceptual_loss": self.perceptual_weight * p_loss,
+                         "sem_loss": sem_loss, "detail_loss": detail_loss, "dependency_loss": dependency_loss,
+                         "vq_loss": codebook_loss[0], "commit_loss": codebook_loss[1], "entropy_loss": codebook_loss[2],
+                         "generator_adv_loss": adaptive * disc_weight * generator_adv_loss,
+                         "disc_adaptive_weight": adaptive, "disc_weight": disc_weight}
+                stats = {k: float(v) for k, v in stats.items()}
+                if log_now:
+                    logger.info("(Generator) " + ", ".join(f"{k}: {v:.4f}" for k, v in stats.items())
+                                + f", codebook_usage: {codebook_loss[3]}")
+                if self.wandb_tracker is not None:
+                    usage = codebook_loss[3]
+                    usage = [float(u) for u in usage] if isinstance(usage, (list, tuple)) else float(usage)
+                    self.wandb_tracker.log(dict(stats, codebook_usage=float(np.mean(usage))), step=global_step)
+            return loss
+        if optimizer_idx == 1:                          # ---- discriminator update (:210-247)
+            logits_fake = self.discriminator(self._disc_in(reconstructions.contiguous().detach(), fade_blur_schedule))
+            logits_real = self.discriminator(self._disc_in(inputs.contiguous().detach(), fade_blur_schedule))
+            if self.lecam_loss_weight is not None:
+                self.lecam_ema.update(logits_real, logits_fake)
+                lecam_loss = lecam_reg(logits_real, logits_fake, self.lecam_ema)
+                d_adversarial_loss = disc_weight * (lecam_loss * self.lecam_loss_weight + self.disc_loss(logits_real, logits_fake))
+            else:
+                d_adversarial_loss = disc_weight * self.disc_loss(logits_real, logits_fake)
+            if log_now or (self.wandb_tracker is not None and global_step % log_every == 0):
+                stats = {"discriminator_adv_loss": float(d_adversarial_loss), "disc_weight": float(disc_weight),
+                         "logits_real": float(logits_real.detach().mean()), "logits_fake": float(logits_fake.detach().mean())}
+                if log_now:
+                    logger.info("(Discriminator) " + ", ".join(f"{k}: {v:.4f}" for k, v in stats.items()))
+                if self.wandb_tracker is not None:
+                    self.wandb_tracker.log(stats, step=global_step)
+            return d_adversarial_loss
+        raise ValueError(f"optimizer_idx must be 0 (generator) or 1 (discriminator), got {optimizer_idx}")

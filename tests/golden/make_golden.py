@@ -324,6 +324,10 @@ def case_loss_stack():
     for k, v in head.state_dict().items():
         d["headw_" + k] = npy(v)
     d["head_y"] = npy(head(acts[0]))
+    from tokenizer.tokenizer_image.discriminator_patchgan import NLayerDiscriminator
+    pg = NLayerDiscriminator(input_nc=3, n_layers=3, ndf=16)
+    d["patchgan_keys"] = np.array(sorted(pg.state_dict().keys()))
+    d["patchgan_shapes"] = np.array([str(tuple(v.shape)) for k, v in sorted(pg.state_dict().items())])
     np.savez_compressed(os.path.join(OUT, "loss_stack.npz"), **d)
     print("loss_stack: aug cases", len(cases), "lpips keys", len(d["lpips_keys"]), "dino acts", len(acts))
 
