@@ -8,9 +8,9 @@
 //                   map per sample; forward and backward are each one tiny per-sample reduction + one elementwise pass
 //                   (the reference: gather through a padded NHWC copy, 3 mean reductions, a mask scatter, ~15 passes).
 //
-// Values only (no index decisions): built with the default -fmad=true.  The weighted channel sums are accumulated in
-// fp64 because the single-pass form  sum w (a/na - b/nb)^2 = Swaa/na^2 + Swbb/nb^2 - 2 Swab/(na nb)  cancels when the
-// reconstruction is close to the input.
+// Values only (no index decisions): built with the default -fmad=true.  The weighted channel sums are folded into fp64
+// (per 8-channel chunk) because the single-pass form  sum w (a/na - b/nb)^2 = Swaa/na^2 + Swbb/nb^2 - 2 Swab/(na nb)
+// cancels when the reconstruction is close to the input.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,11 +20,6 @@
 namespace xql {
 
 constexpr int LP_THREADS = 256;
-
-__device__ __forceinline__ float ldf(const float *p) { return *p; }
-__device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
-__device__ __forceinline__ void stf(float *p, float v) { *p = v; }
-__device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T *sh) {
@@ -45,35 +40,67 @@ __device__ __forceinline__ T block_sum(T v, T *sh) {
 
 struct PixSums { float saa, sbb; double waa, wbb, wab; };
 
-// one pass over the C channels of pixel p of image b (consecutive threads = consecutive pixels -> coalesced)
+// NP pixels per thread: 1 for fp32 maps (4-byte loads), 2 for bf16 maps (one 4-byte bf16x2 load covers two adjacent
+// pixels, so a warp still moves 128 contiguous bytes per load instruction).
+template <typename T> struct PixVec;
+template <> struct PixVec<float> {
+    static constexpr int NP = 1;
+    __device__ static __forceinline__ void load(const float *p, float (&v)[1]) { v[0] = *p; }
+    __device__ static __forceinline__ void store(float *p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct PixVec<__nv_bfloat16> {
+    static constexpr int NP = 2;
+    __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[2]) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p));
+        v[0] = f.x; v[1] = f.y;
+    }
+    __device__ static __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[2]) {
+        *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(v[0], v[1]);
+    }
+};
+
+// One pass over the C channels of NP adjacent pixels (consecutive threads = consecutive pixels -> coalesced).  The
+// weighted sums are accumulated in fp32 over chunks of LP_CHUNK channels and folded into fp64 once per chunk: the
+// fp64 conversions were the bottleneck of the first version (1.8 TB/s), and the final combination
+//   Swaa/na^2 + Swbb/nb^2 - 2 Swab/(na nb)   still sees sums that carry ~1e-7 relative error.
+constexpr int LP_CHUNK = 8;
 template <typename T>
-__device__ __forceinline__ PixSums pixel_sums(const T *__restrict__ f0, const T *__restrict__ f1, const float *__restrict__ w,
-                                              int C, int HW) {
-    PixSums s = {0.f, 0.f, 0.0, 0.0, 0.0};
-    int c = 0;
-    for (; c + 4 <= C; c += 4) {                  // 8 independent loads in flight per thread
-        float a[4], b[4];
+__device__ __forceinline__ void pixel_sums(const T *__restrict__ f0, const T *__restrict__ f1, const float *__restrict__ w,
+                                           int C, int HW, PixSums (&s)[PixVec<T>::NP]) {
+    constexpr int NP = PixVec<T>::NP;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a[u] = ldf(f0 + (size_t)(c + u) * HW); b[u] = ldf(f1 + (size_t)(c + u) * HW); }
+    for (int q = 0; q < NP; ++q) s[q] = PixSums{0.f, 0.f, 0.0, 0.0, 0.0};
+    for (int c0 = 0; c0 < C; c0 += LP_CHUNK) {
+        float a[LP_CHUNK][NP], b[LP_CHUNK][NP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float wc = w[c + u];
-            s.saa = fmaf(a[u], a[u], s.saa);
-            s.sbb = fmaf(b[u], b[u], s.sbb);
-            s.waa += (double)(wc * a[u]) * (double)a[u];
-            s.wbb += (double)(wc * b[u]) * (double)b[u];
-            s.wab += (double)(wc * a[u]) * (double)b[u];
+        for (int u = 0; u < LP_CHUNK; ++u) {               // 2 * LP_CHUNK independent loads in flight per thread
+            if (c0 + u < C) {
+                PixVec<T>::load(f0 + (size_t)(c0 + u) * HW, a[u]);
+                PixVec<T>::load(f1 + (size_t)(c0 + u) * HW, b[u]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { a[u][q] = 0.f; b[u][q] = 0.f; }
+            }
         }
+        float waa[NP], wbb[NP], wab[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) waa[q] = wbb[q] = wab[q] = 0.f;
+#pragma unroll
+        for (int u = 0; u < LP_CHUNK; ++u) {
+            const float wc = (c0 + u < C) ? w[c0 + u] : 0.f;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const float wa = wc * a[u][q], wb = wc * b[u][q];
+                s[q].saa = fmaf(a[u][q], a[u][q], s[q].saa);
+                s[q].sbb = fmaf(b[u][q], b[u][q], s[q].sbb);
+                waa[q] = fmaf(wa, a[u][q], waa[q]);
+                wbb[q] = fmaf(wb, b[u][q], wbb[q]);
+                wab[q] = fmaf(wa, b[u][q], wab[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { s[q].waa += (double)waa[q]; s[q].wbb += (double)wbb[q]; s[q].wab += (double)wab[q]; }
     }
-    for (; c < C; ++c) {
-        const float a = ldf(f0 + (size_t)c * HW), b = ldf(f1 + (size_t)c * HW), wc = w[c];
-        s.saa = fmaf(a, a, s.saa);
-        s.sbb = fmaf(b, b, s.sbb);
-        s.waa += (double)(wc * a) * (double)a;
-        s.wbb += (double)(wc * b) * (double)b;
-        s.wab += (double)(wc * a) * (double)b;
-    }
-    return s;
 }
 
 // partial[b][blk] = sum over the CTA's pixels of  sum_c w_c (a_c/(|a|+eps) - b_c/(|b|+eps))^2
@@ -81,14 +108,19 @@ template <typename T>
 __global__ void __launch_bounds__(LP_THREADS)
 lpips_layer_fwd_kernel(const T *__restrict__ f0, const T *__restrict__ f1, const float *__restrict__ w, int C, int HW,
                        float eps, double *__restrict__ partial) {
+    constexpr int NP = PixVec<T>::NP;
     __shared__ double sh[LP_THREADS / 32];
-    const int b = blockIdx.y, p = blockIdx.x * LP_THREADS + threadIdx.x;
+    const int b = blockIdx.y, p = (blockIdx.x * LP_THREADS + threadIdx.x) * NP;
     double val = 0.0;
-    if (p < HW) {
+    if (p < HW) {                                          // HW % NP == 0 (checked by the launcher)
         const size_t base = (size_t)b * C * HW + p;
-        const PixSums s = pixel_sums(f0 + base, f1 + base, w, C, HW);
-        const double na = (double)(sqrtf(s.saa) + eps), nb = (double)(sqrtf(s.sbb) + eps);
-        val = s.waa / (na * na) + s.wbb / (nb * nb) - 2.0 * s.wab / (na * nb);
+        PixSums s[NP];
+        pixel_sums<T>(f0 + base, f1 + base, w, C, HW, s);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const double na = (double)(sqrtf(s[q].saa) + eps), nb = (double)(sqrtf(s[q].sbb) + eps);
+            val += s[q].waa / (na * na) + s[q].wbb / (nb * nb) - 2.0 * s[q].wab / (na * nb);
+        }
     }
     val = block_sum(val, sh);
     if (threadIdx.x == 0) partial[(size_t)b * gridDim.x + blockIdx.x] = val;
@@ -113,21 +145,35 @@ template <typename T>
 __global__ void __launch_bounds__(LP_THREADS)
 lpips_layer_bwd_kernel(const T *__restrict__ f0, const T *__restrict__ f1, const float *__restrict__ w, int C, int HW,
                        float eps, const float *__restrict__ g_out, T *__restrict__ g_f1) {
-    const int b = blockIdx.y, p = blockIdx.x * LP_THREADS + threadIdx.x;
+    constexpr int NP = PixVec<T>::NP;
+    const int b = blockIdx.y, p = (blockIdx.x * LP_THREADS + threadIdx.x) * NP;
     if (p >= HW) return;
     const size_t base = (size_t)b * C * HW + p;
-    const PixSums s = pixel_sums(f0 + base, f1 + base, w, C, HW);
-    const float nb0 = sqrtf(s.sbb);
-    const float na = sqrtf(s.saa) + eps, nb = nb0 + eps;
-    const float Tsum = (float)(2.0 * (s.wbb / (double)nb - s.wab / (double)na));
-    // the reference differentiates sqrt(sum b^2): at an all-zero pixel that is 0 * inf = NaN; here the norm term is dropped
-    const float kb = nb0 > 0.f ? Tsum / (nb * nb * nb0) : 0.f;
+    PixSums s[NP];
+    pixel_sums<T>(f0 + base, f1 + base, w, C, HW, s);
+    float ra[NP], rb[NP], kb[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const float nb0 = sqrtf(s[q].sbb);
+        const float na = sqrtf(s[q].saa) + eps, nb = nb0 + eps;
+        const float Tsum = (float)(2.0 * (s[q].wbb / (double)nb - s[q].wab / (double)na));
+        // the reference differentiates sqrt(sum b^2): at an all-zero pixel that is 0 * inf = NaN; here the norm term is dropped
+        kb[q] = nb0 > 0.f ? Tsum / (nb * nb * nb0) : 0.f;
+        ra[q] = 1.f / na; rb[q] = 1.f / nb;
+    }
     const float gs = g_out[b] / (float)HW;
-    const float ra = 1.f / na, rb = 1.f / nb;
+#pragma unroll 4
     for (int c = 0; c < C; ++c) {               // second pass: L1 / L2 hits for the narrow stages, HBM for the wide ones
-        const float a = ldf(f0 + base + (size_t)c * HW), bv = ldf(f1 + base + (size_t)c * HW);
-        const float d = bv * rb - a * ra;
-        stf(g_f1 + base + (size_t)c * HW, gs * (2.f * w[c] * d * rb - bv * kb));
+        float a[NP], bv[NP], o[NP];
+        PixVec<T>::load(f0 + base + (size_t)c * HW, a);
+        PixVec<T>::load(f1 + base + (size_t)c * HW, bv);
+        const float w2 = 2.f * w[c];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const float d = bv[q] * rb[q] - a[q] * ra[q];
+            o[q] = gs * (w2 * d * rb[q] - bv[q] * kb[q]);
+        }
+        PixVec<T>::store(g_f1 + base + (size_t)c * HW, o);
     }
 }
 
@@ -272,8 +318,10 @@ int xq_lpips_layer_forward(const void *f0, const void *f1, int is_bf16, const fl
                            int accumulate, float *out, void *workspace, size_t workspace_bytes, void *stream) {
     if (!f0 || !f1 || !lin_w || !out || !workspace || B <= 0 || C <= 0 || HW <= 0) return XQ_ERR_ARG;
     if (workspace_bytes < xq_lpips_workspace_bytes(B, HW)) return XQ_ERR_WORKSPACE;
+    if (is_bf16 && (HW & 1)) return XQ_ERR_UNSUPPORTED;   // bf16 maps are read as bf16x2 pixel pairs
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (HW + LP_THREADS - 1) / LP_THREADS;
+    const int np = is_bf16 ? 2 : 1;
+    const int nblk = (HW / np + LP_THREADS - 1) / LP_THREADS;
     dim3 grid(nblk, B);
     if (is_bf16)
         lpips_layer_fwd_kernel<<<grid, LP_THREADS, 0, st>>>((const __nv_bfloat16 *)f0, (const __nv_bfloat16 *)f1, lin_w, C, HW, eps,
@@ -289,8 +337,9 @@ int xq_lpips_layer_forward(const void *f0, const void *f1, int is_bf16, const fl
 int xq_lpips_layer_backward(const void *f0, const void *f1, int is_bf16, const float *lin_w, int B, int C, int HW, float eps,
                             const float *g_out, void *g_f1, void *stream) {
     if (!f0 || !f1 || !lin_w || !g_out || !g_f1 || B <= 0 || C <= 0 || HW <= 0) return XQ_ERR_ARG;
+    if (is_bf16 && (HW & 1)) return XQ_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((HW + LP_THREADS - 1) / LP_THREADS, B);
+    dim3 grid((HW / (is_bf16 ? 2 : 1) + LP_THREADS - 1) / LP_THREADS, B);
     if (is_bf16)
         lpips_layer_bwd_kernel<<<grid, LP_THREADS, 0, st>>>((const __nv_bfloat16 *)f0, (const __nv_bfloat16 *)f1, lin_w, C, HW, eps,
                                                             g_out, (__nv_bfloat16 *)g_f1);

@@ -15,7 +15,8 @@ class _LpipsStage(torch.autograd.Function):
     def forward(ctx, f0, f1, lin_w, eps: float):
         if f0.shape != f1.shape or f0.dim() != 4:
             raise ValueError(f"feature maps must have the same [B,C,H,W] shape, got {tuple(f0.shape)} / {tuple(f1.shape)}")
-        dt = torch.bfloat16 if (f0.dtype == torch.bfloat16 and f1.dtype == torch.bfloat16) else torch.float32
+        dt = torch.bfloat16 if (f0.dtype == torch.bfloat16 and f1.dtype == torch.bfloat16
+                                and (f0.shape[2] * f0.shape[3]) % 2 == 0) else torch.float32   # bf16 kernel reads pixel pairs
         f0, f1 = f0.to(dt).contiguous(), f1.to(dt).contiguous()
         w = lin_w.detach().reshape(-1).float().contiguous()
         B, Cc, H, W = f0.shape

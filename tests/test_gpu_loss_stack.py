@@ -155,10 +155,13 @@ def test_vqloss_dinodisc_generator_and_discriminator_steps():
     g_loss.backward()
     assert torch.isfinite(last.grad).all() and float(last.grad.abs().sum()) > 0
     assert all(p.grad is None for p in loss.perceptual_loss.parameters())
+    import random
     torch.manual_seed(6)
+    random.seed(6)          # the frozen backbone picks "random 224-crop" vs "area resize" with Python's RNG (:331)
     d_loss = loss(cb, None, None, None, x, rec.detach(), 1, 1)
     # replay the same augmentation draws and rebuild the discriminator objective by hand
     torch.manual_seed(6)
+    random.seed(6)
     lf = loss.discriminator(loss.daug.aug(rec.detach(), 0))
     lr = loss.discriminator(loss.daug.aug(x, 0))
     want = lecam_reg(lr, lf, loss.lecam_ema) * 0.001 + hinge_d_loss(lr, lf)
