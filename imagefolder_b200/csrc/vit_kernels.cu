@@ -383,9 +383,20 @@ __device__ __forceinline__ float gelu_f(float x) {
     const float h = 0.5f * x;
     return fmaf(-fabsf(h), rcp_fast(p), h + fabsf(h));
 }
+// gelu'(x) = Phi(x) + x phi(x).  Both need exp(-x^2/2): with A&S 7.1.26,  erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),
+// t = 1/(1 + p z), the SAME exponential serves Phi and phi (z = |x|/sqrt2), so the derivative costs one ex2 + one rcp +
+// ~14 FP32 instructions (the 7.1.28 erf + a separate exp used before: ~20).  |abs err| 3e-7.
 __device__ __forceinline__ float dgelu_f(float x) {
-    const float e = ex2_fast(x * x * -0.72134752044448170f);      // exp(-x^2 / 2)
-    return fmaf(0.5f, erf_as(x * 0.70710678118654752f), 0.5f) + x * 0.3989422804014327f * e;
+    const float ax = fabsf(x);
+    const float t = rcp_fast(fmaf(ax, 0.23164189f, 1.0f));             // p / sqrt2 = 0.3275911 / 1.41421356
+    float q = fmaf(t, 1.061405429f, -1.453152027f);
+    q = fmaf(q, t, 1.421413741f);
+    q = fmaf(q, t, -0.284496736f);
+    q = fmaf(q, t, 0.254829592f);
+    const float e = ex2_fast(x * x * -0.72134752044448170f);            // exp(-x^2 / 2)
+    const float pe = q * t * e;                                          // 1 - erf(|x| / sqrt2)
+    const float half = fmaf(-0.5f, pe, 0.5f);                           // Phi(|x|) - 1/2
+    return fmaf(x * 0.3989422804014327f, e, 0.5f + copysignf(half, x));
 }
 
 // y = gelu(x + bias).  A thread owns column chunk c (8 bf16 = 16 B) and walks rows with a grid stride, RU rows
@@ -605,6 +616,61 @@ static int persistent_grid(K kernel, int threads, size_t smem = 0) {
     return sms * per_sm;
 }
 
+// Token assembly (dinov2.py:151-170 / 318-336): the encoder / decoder build their input sequence as
+//   [prefix | image tokens | latent tokens] + positional / level embeddings
+// with cat + add + cat + add over [B, T, D] fp32 tensors.  Everything except ONE block of rows (the patch tokens in the
+// encoder, the quantised latents in the decoder) is batch-independent, so the sequence is
+//   out[b, t, :] = table[t, :] + (t0 <= t < t0 + Ls ? src[b, t - t0, :] : 0)
+// where `table` [T, D] is the module's own assembly evaluated once on a zero input of batch 1 (host side, autograd intact).
+// fwd: one pass (read src, write out).  bwd: ONE read of g produces d_src (cast to the source dtype) and d_table = sum_b g.
+template <typename TS>
+__global__ void assemble_fwd_kernel(const TS *__restrict__ src, const float *__restrict__ table, int Ls, int T, int D4, int t0,
+                                    float *__restrict__ out, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int d4 = (int)(i % D4);
+    const size_t bt = i / D4;
+    const int t = (int)(bt % T);
+    const size_t b = bt / T;
+    float4 v = *reinterpret_cast<const float4 *>(table + ((size_t)t * D4 + d4) * 4);
+    if (t >= t0 && t < t0 + Ls) {
+        const size_t so = ((b * Ls + (t - t0)) * D4 + d4) * 4;
+        float4 sv;
+        if (sizeof(TS) == 2) sv = load_bf16x4(reinterpret_cast<const __nv_bfloat16 *>(src) + so);
+        else sv = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(src) + so);
+        v.x += sv.x; v.y += sv.y; v.z += sv.z; v.w += sv.w;
+    }
+    *reinterpret_cast<float4 *>(out + i * 4) = v;
+}
+
+template <typename TS>
+__global__ void assemble_bwd_kernel(const float *__restrict__ g, int B, int Ls, int T, int D4, int t0, TS *__restrict__ d_src,
+                                    float *__restrict__ d_table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (t, d4)
+    if (i >= T * D4) return;
+    const int t = i / D4, d4 = i - t * D4;
+    const bool in_src = d_src && t >= t0 && t < t0 + Ls;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = (size_t)T * D4 * 4;
+    const float *gp = g + ((size_t)t * D4 + d4) * 4;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = (b0 + u < B) ? *reinterpret_cast<const float4 *>(gp + (size_t)(b0 + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            if (in_src && b0 + u < B) {
+                const size_t so = (((size_t)(b0 + u) * Ls + (t - t0)) * D4 + d4) * 4;
+                if (sizeof(TS) == 2) store_bf16x4(reinterpret_cast<__nv_bfloat16 *>(d_src) + so, v[u]);
+                else *reinterpret_cast<float4 *>(reinterpret_cast<float *>(d_src) + so) = v[u];
+            }
+        }
+    }
+    if (d_table) *reinterpret_cast<float4 *>(d_table + ((size_t)t * D4 + d4) * 4) = acc;
+}
+
 static int bwd_grid() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -695,6 +761,29 @@ int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, 
         return XQ_ERR_CUDA;
     pack_qkv_kernel<<<grid, PACK_THREADS, smem, st>>>((const uint4 *)dq, (const uint4 *)dk, (const uint4 *)dv,
                                                       (uint4 *)dqkv, g_bias, counter, (int)M, C8);
+    return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
+}
+
+int xq_vit_assemble_fwd(const void *src, int src_is_bf16, const float *table, int B, int Ls, int T, int D, int t0, float *out,
+                        void *stream) {
+    if (!src || !table || !out || B <= 0 || Ls <= 0 || T <= 0 || D <= 0 || (D & 3) || t0 < 0 || t0 + Ls > T) return XQ_ERR_ARG;
+    const size_t total4 = (size_t)B * T * (D / 4);
+    const unsigned grid = (unsigned)((total4 + 255) / 256);
+    if (src_is_bf16)
+        assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)src, table, Ls, T, D / 4, t0, out, total4);
+    else
+        assemble_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)src, table, Ls, T, D / 4, t0, out, total4);
+    return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
+}
+
+int xq_vit_assemble_bwd(const float *g, int B, int Ls, int T, int D, int t0, void *d_src, int src_is_bf16, float *d_table,
+                        void *stream) {
+    if (!g || (!d_src && !d_table) || B <= 0 || Ls <= 0 || T <= 0 || D <= 0 || (D & 3) || t0 < 0 || t0 + Ls > T) return XQ_ERR_ARG;
+    const int n = T * (D / 4);
+    if (src_is_bf16)
+        assemble_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, B, Ls, T, D / 4, t0, (__nv_bfloat16 *)d_src, d_table);
+    else
+        assemble_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(g, B, Ls, T, D / 4, t0, (float *)d_src, d_table);
     return cudaGetLastError() == cudaSuccess ? XQ_OK : XQ_ERR_CUDA;
 }
 

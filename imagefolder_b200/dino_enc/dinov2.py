@@ -12,7 +12,7 @@ import math
 import torch
 import torch.nn as nn
 
-from ..vit_ops import patch_embed, run_blocks
+from ..vit_ops import assemble_tokens, patch_embed, run_blocks
 from .to_pixel import ToPixel
 from .vision_transformer import Attention, create_model, trunc_normal_
 
@@ -90,9 +90,15 @@ class DINOv2Encoder(nn.Module):
     def no_weight_decay(self):
         return ['model.pos_embed', 'model.cls_token', 'model.dist_token', 'latent_tokens', 'latent_pos_embed']
 
-    def forward(self, x, masks=None):
-        """dinov2.py:146-198 -> [B, num_latent_tokens, D]"""
-        x = patch_embed(self.model.patch_embed, x)
+    def _assembly_is_static(self):
+        """no stochastic op between the patch tokens and the blocks (pos_drop / patch_drop inactive)"""
+        m = self.model
+        return (isinstance(m.patch_drop, nn.Identity)
+                and (not self.training or getattr(m.pos_drop, "p", 0.0) == 0.0) and not m.no_embed_class)
+
+    def _assemble(self, x):
+        """dinov2.py:151-170: [cls | patch tokens] + pos-embed, then the latent tokens (+ their resampled pos-embed) and the
+        level embedding.  x: patch tokens [B, N, D] -> fp32 [B, 1 + N + L, D]."""
         with _autocast_off(x):
             x = self.model._pos_embed(x)
             x = self.model.patch_drop(x)
@@ -116,6 +122,15 @@ class DINOv2Encoder(nn.Module):
                         x += self.lvl_embed(self.lvl1LC.expand(x.size(0), -1))
                 else:
                     x = torch.cat([x, z + self.latent_pos_embed], dim=1)
+        return x
+
+    def forward(self, x, masks=None):
+        """dinov2.py:146-198 -> [B, num_latent_tokens, D]"""
+        x = patch_embed(self.model.patch_embed, x)
+        if self._assembly_is_static():
+            x = assemble_tokens(self, self._assemble, x, self.num_prefix_tokens)
+        else:
+            x = self._assemble(x)
         # norm_pre -> blocks -> norm (dinov2.py:176-190); fused CUDA glue under bf16 autocast
         x = run_blocks(self.model, x, self.attn_mask if self.use_attn_mask else None)
         if self.num_latent_tokens:
@@ -186,8 +201,9 @@ class DINOv2Decoder(nn.Module):
     def last_layer(self):
         return self.to_pixel.model.weight
 
-    def forward(self, z):
-        """dinov2.py:313-365: z [B, L, D] -> image [B, 3, H, W]"""
+    def _assemble(self, z):
+        """dinov2.py:318-336: [cls | mask tokens] + pos-embed, then the latents (with their own cls slot and resampled
+        pos-embed when abs_pos_embed) and the level embedding.  z [B, L, D] -> fp32 [B, T, D]."""
         x = self.mask_token.expand(z.size(0), self.num_img_tokens, -1)
         with _autocast_off(x):
             x = self.model._pos_embed(x)
@@ -202,6 +218,18 @@ class DINOv2Decoder(nn.Module):
             x = torch.cat([x, z], dim=1)
             if self.abs_pos_embed:
                 x += self.lvl_embed(self.lvl1LC.expand(x.size(0), -1))
+        return x
+
+    def forward(self, z):
+        """dinov2.py:313-365: z [B, L, D] -> image [B, 3, H, W]"""
+        m = self.model
+        static = isinstance(m.patch_drop, nn.Identity) and (not self.training or getattr(m.pos_drop, "p", 0.0) == 0.0) \
+            and not m.no_embed_class
+        if static:
+            t0 = self.num_img_tokens + self.num_prefix_tokens + (self.num_prefix_tokens if self.abs_pos_embed else 0)
+            x = assemble_tokens(self, self._assemble, z, t0)
+        else:
+            x = self._assemble(z)
         x = run_blocks(self.model, x)
         x = x[:, self.num_prefix_tokens:self.num_img_tokens + self.num_prefix_tokens]
         return self.to_pixel(x)

@@ -219,6 +219,14 @@ int xq_vit_pack_qkv(const void *dq, const void *dk, const void *dv, void *dqkv, 
  *   x fp32 [B,Cin,H,W] -> patches bf16 [B*(H/p)*(W/p), Cin*p*p] (K index = (c*p + ky)*p + kx = the flattened conv
  *   weight), so that tokens = patches @ weight.view(D,-1)^T + bias is a plain GEMM.  p % 4 == 0, H % p == W % p == 0. */
 int xq_vit_patchify(const float *x, void *patches, int B, int Cin, int H, int W, int p, void *stream);
+/*   token assembly of the ViT encoder / decoder input (dino_enc/dinov2.py:151-170, 318-336):
+ *     out[b,t,:] = table[t,:] + (t0 <= t < t0+Ls ? src[b,t-t0,:] : 0)   out fp32 [B,T,D], table fp32 [T,D] (the batch-
+ *   independent part: cls / mask / latent tokens + positional + level embeddings), src [B,Ls,D] fp32 or bf16.
+ *   backward: d_src = g[:, t0:t0+Ls] in the source dtype (may be NULL), d_table = sum_b g (may be NULL); one read of g. */
+int xq_vit_assemble_fwd(const void *src, int src_is_bf16, const float *table, int B, int Ls, int T, int D, int t0, float *out,
+                        void *stream);
+int xq_vit_assemble_bwd(const float *g, int B, int Ls, int T, int D, int t0, void *d_src, int src_is_bf16, float *d_table,
+                        void *stream);
 /*   y = GELU(x + bias) exact-erf form (timm Mlp act_layer=nn.GELU), x / y bf16 [M,C], bias fp32 [C] or NULL,
  *   C % 8 == 0.  Backward also returns g_bias [C] = column sums of gx (may be NULL). */
 int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, void *stream);

@@ -201,6 +201,7 @@ class EagerTokenizer(torch.nn.Module):
         m = self.m
         saved, saved_pe = vit_ops.fused_path_ok, vit_ops.patch_embed_ok
         vit_ops.fused_path_ok = vit_ops.patch_embed_ok = lambda *a, **k: False
+        saved_as, vit_ops.ASSEMBLE_ENABLED[0] = vit_ops.ASSEMBLE_ENABLED[0], False
         try:
             h = m.encode(x)
             b, c, l, _ = h.shape
@@ -228,4 +229,5 @@ class EagerTokenizer(torch.nn.Module):
             dec = m.decode(quant)
         finally:
             vit_ops.fused_path_ok, vit_ops.patch_embed_ok = saved, saved_pe
+            vit_ops.ASSEMBLE_ENABLED[0] = saved_as
         return dec, (vq, cm, en, usages), None, None, 0.0

@@ -228,3 +228,68 @@ def test_patch_embed_gemm_matches_conv():
     L = _capi.lib()
     assert L.xq_vit_patchify(None, None, 1, 3, 64, 64, 16, None) != 0
     assert L.xq_vit_patchify(_capi.ptr(xg.detach()), _capi.ptr(xg.detach()), 1, 3, 64, 64, 6, None) != 0
+
+
+@pytest.mark.parametrize("pq,abs_pe", [(1, True), (2, True), (1, False)])
+def test_fused_token_assembly_equals_module_chain(pq, abs_pe):
+    """encoder / decoder input sequence through xq_vit_assemble_* == the module's own cat / add chain: outputs and the
+    gradients of every parameter that feeds the sequence (cls / mask / latent tokens, pos-embed, level embedding)."""
+    from imagefolder_b200.dino_enc import DINOv2Decoder, DINOv2Encoder
+    from imagefolder_b200 import vit_ops
+    kw = {'img_size': 256, 'patch_size': 16, 'drop_path_rate': 0.0}   # the level-embedding table assumes 16 x 16 image tokens
+    torch.manual_seed(pq)
+    L = 16 * pq if pq > 1 else 16
+    enc = DINOv2Encoder(num_latent_tokens=L, model_name='vit_small_patch14_dinov2.lvd142m', model_kwargs=kw, tuning_method='full',
+                        abs_pos_embed=abs_pe, product_quant=pq).cuda().train()
+    dec = DINOv2Decoder(num_latent_tokens=16, model_name='vit_small_patch14_dinov2.lvd142m', model_kwargs=kw, tuning_method='full',
+                        abs_pos_embed=abs_pe).cuda().train()
+    x = torch.rand(2, 3, 256, 256, device="cuda") * 2 - 1
+    z = torch.randn(2, 16, dec.embed_dim, device="cuda").to(torch.bfloat16).requires_grad_(True)
+
+    def run(fused):
+        vit_ops.ASSEMBLE_ENABLED[0] = fused
+        try:
+            for m in (enc, dec):
+                m.zero_grad(set_to_none=True)
+            if z.grad is not None:
+                z.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                he = enc(x)
+                hd = dec(z)
+            torch.manual_seed(99)
+            (he.float() * torch.randn_like(he.float())).sum().add((hd.float() * torch.randn_like(hd.float())).sum()).backward()
+            grads = {n: p.grad.clone() for mod, tag in ((enc, "enc."), (dec, "dec.")) for n_, p in mod.named_parameters()
+                     if p.grad is not None for n in [tag + n_]
+                     if any(k in n_ for k in ("cls_token", "pos_embed", "latent_tokens", "lvl_embed", "mask_token", "latent_pos_embed",
+                                              "patch_embed.proj"))}
+            return he.detach().float(), hd.detach().float(), z.grad.clone().float(), grads
+        finally:
+            vit_ops.ASSEMBLE_ENABLED[0] = True
+
+    he1, hd1, gz1, g1 = run(True)
+    assert getattr(enc, "_assemble_ok", None) is True and getattr(dec, "_assemble_ok", None) is True
+    he0, hd0, gz0, g0 = run(False)
+    tol = dict(rtol=3e-2, atol=3e-2)          # bf16 pipelines: identical up to rounding order of the fp32 adds feeding bf16 GEMMs
+    np.testing.assert_allclose(he1.cpu().numpy(), he0.cpu().numpy(), **tol)
+    np.testing.assert_allclose(hd1.cpu().numpy(), hd0.cpu().numpy(), **tol)
+    np.testing.assert_allclose(gz1.cpu().numpy(), gz0.cpu().numpy(), rtol=5e-2, atol=5e-2 * float(gz0.abs().max()))
+    assert set(g1) == set(g0) and len(g1) >= 6
+    for k in g0:
+        a, b = g1[k].float().cpu().numpy(), g0[k].float().cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=5e-2, atol=5e-2 * float(np.abs(b).max()) + 1e-6, err_msg=k)
+
+
+def test_assemble_cabi_exact():
+    from imagefolder_b200.vit_ops import _Assemble
+    torch.manual_seed(0)
+    for dt in (torch.float32, torch.bfloat16):
+        src = torch.randn(5, 7, 24, device="cuda").to(dt).requires_grad_(True)
+        table = torch.randn(12, 24, device="cuda", requires_grad=True)
+        out = _Assemble.apply(src, table, 3)
+        ref = table.detach().unsqueeze(0).repeat(5, 1, 1)
+        ref[:, 3:10] += src.detach().float()
+        assert torch.equal(out, ref)
+        g = torch.randn_like(out)
+        gs, gt = torch.autograd.grad(out, (src, table), g)
+        assert gs.dtype == dt and torch.equal(gs, g[:, 3:10].to(dt))
+        np.testing.assert_allclose(gt.cpu().numpy(), g.sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6)
