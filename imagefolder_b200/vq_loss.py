@@ -20,57 +20,64 @@ from .lpips import LPIPS
 
 
 # ---- GAN objectives (vq_loss.py:18-45) -------------------------------------------------------------------------------
+def _bce_const_input(const: float, logits):
+    """BCE-with-logits exactly as the reference CALLS it (:33-34, :44): the constant tensor sits in the *input* slot and the
+    logits in the *target* slot."""
+    return F.binary_cross_entropy_with_logits(torch.full_like(logits, const), logits).mean()
+
+
 def hinge_d_loss(logits_real, logits_fake):
-    return 0.5 * (torch.mean(F.relu(1. - logits_real)) + torch.mean(F.relu(1. + logits_fake)))
+    margin_real = F.relu(1. - logits_real).mean()
+    margin_fake = F.relu(1. + logits_fake).mean()
+    return (margin_real + margin_fake) * 0.5
 
 
 def vanilla_d_loss(logits_real, logits_fake):
-    return 0.5 * (torch.mean(F.softplus(-logits_real)) + torch.mean(F.softplus(logits_fake)))
+    return (F.softplus(-logits_real).mean() + F.softplus(logits_fake).mean()) * 0.5
 
 
 def non_saturating_d_loss(logits_real, logits_fake):
-    # argument order as in the reference (:33-34): the constant tensor is the *input*, the logits are the *target*
-    real = torch.mean(F.binary_cross_entropy_with_logits(torch.ones_like(logits_real), logits_real))
-    fake = torch.mean(F.binary_cross_entropy_with_logits(torch.zeros_like(logits_fake), logits_fake))
-    return 0.5 * (real + fake)
+    return (_bce_const_input(1.0, logits_real) + _bce_const_input(0.0, logits_fake)) * 0.5
 
 
 def hinge_gen_loss(logit_fake):
-    return -torch.mean(logit_fake)
+    return logit_fake.mean().neg()
 
 
 def non_saturating_gen_loss(logit_fake):
-    return torch.mean(F.binary_cross_entropy_with_logits(torch.ones_like(logit_fake), logit_fake))
+    return _bce_const_input(1.0, logit_fake)
 
 
 def adopt_weight(weight, global_step, threshold=0, value=0.):
-    return value if global_step < threshold else weight
+    """`value` until the discriminator starts (:47-50)."""
+    return weight if global_step >= threshold else value
 
 
 def anneal_weight(weight, global_step, threshold=0, initial_value=0.3, final_value=0.1, anneal_steps=2000):
-    if global_step < threshold:
+    """linear ramp initial -> final over `anneal_steps` after `threshold` (:52-62)."""
+    done = (global_step - threshold) / anneal_steps
+    if done < 0:
         return initial_value
-    if global_step < threshold + anneal_steps:
-        return initial_value - (global_step - threshold) / anneal_steps * (initial_value - final_value)
-    return final_value
+    return final_value if done >= 1 else initial_value + done * (final_value - initial_value)
 
 
 class LeCAM_EMA(object):
     """running means of the real / fake logits (:64-73); kept as 0-dim tensors on the logits' device (no host sync)."""
 
     def __init__(self, init=0., decay=0.999):
-        self.logits_real_ema = init
-        self.logits_fake_ema = init
         self.decay = decay
+        self.logits_real_ema = self.logits_fake_ema = init
 
     def update(self, logits_real, logits_fake):
-        self.logits_real_ema = self.logits_real_ema * self.decay + logits_real.detach().float().mean() * (1 - self.decay)
-        self.logits_fake_ema = self.logits_fake_ema * self.decay + logits_fake.detach().float().mean() * (1 - self.decay)
+        keep, new = self.decay, 1 - self.decay
+        self.logits_real_ema = keep * self.logits_real_ema + new * logits_real.detach().float().mean()
+        self.logits_fake_ema = keep * self.logits_fake_ema + new * logits_fake.detach().float().mean()
 
 
 def lecam_reg(real_pred, fake_pred, lecam_ema):
-    return torch.mean(F.relu(real_pred - lecam_ema.logits_fake_ema).pow(2)) + \
-        torch.mean(F.relu(lecam_ema.logits_real_ema - fake_pred).pow(2))
+    over = F.relu(real_pred - lecam_ema.logits_fake_ema).square().mean()
+    under = F.relu(lecam_ema.logits_real_ema - fake_pred).square().mean()
+    return over + under
 
 
 class PatchGANDiscriminator(nn.Module):
@@ -157,56 +164,59 @@ class VQLoss(nn.Module):
             return x
         return self.daug.aug(x, 0 if fade_blur_schedule < 1e-6 else fade_blur_schedule)
 
+    def _log(self, tag, stats, logger, global_step, extra=""):
+        stats = {k: float(v) for k, v in stats.items()}
+        if logger is not None:
+            logger.info(f"({tag}) " + ", ".join(f"{k}: {v:.4f}" for k, v in stats.items()) + extra)
+        if self.wandb_tracker is not None:
+            self.wandb_tracker.log(stats, step=global_step)
+
+    def _generator_step(self, codebook_loss, extras, inputs, recon, global_step, last_layer, disc_weight, fade, log):
+        """vq_loss.py:153-207"""
+        rec = self.rec_loss(inputs, recon)
+        perceptual = self.perceptual_loss(inputs, recon).mean()
+        adv = self.gen_adv_loss(self.discriminator(self._disc_in(recon, fade)))
+        if self.disc_adaptive_weight:
+            nll = self.rec_weight * rec + self.perceptual_weight * perceptual
+            balance = self.calculate_adaptive_weight(nll, adv, last_layer=last_layer)
+        else:
+            balance = 1
+        sem, detail, dep = (0 if e is None else e for e in extras)
+        total = self.rec_weight * rec + self.perceptual_weight * perceptual + balance * disc_weight * adv \
+            + codebook_loss[0] + codebook_loss[1] + codebook_loss[2] + sem + detail + dep
+        if log:
+            self._log("Generator", {"rec_loss": self.rec_weight * rec, "perceptual_loss": self.perceptual_weight * perceptual,
+                                    "sem_loss": sem, "detail_loss": detail, "dependency_loss": dep,
+                                    "vq_loss": codebook_loss[0], "commit_loss": codebook_loss[1],
+                                    "entropy_loss": codebook_loss[2], "generator_adv_loss": balance * disc_weight * adv,
+                                    "disc_adaptive_weight": balance, "disc_weight": disc_weight},
+                      log if log is not True else None, global_step, extra=f", codebook_usage: {codebook_loss[3]}")
+        return total
+
+    def _discriminator_step(self, inputs, recon, global_step, disc_weight, fade, log):
+        """vq_loss.py:210-247"""
+        fake = self.discriminator(self._disc_in(recon.detach(), fade))
+        real = self.discriminator(self._disc_in(inputs.detach(), fade))
+        objective = self.disc_loss(real, fake)
+        if self.lecam_loss_weight is not None:
+            self.lecam_ema.update(real, fake)
+            objective = lecam_reg(real, fake, self.lecam_ema) * self.lecam_loss_weight + objective
+        d_loss = disc_weight * objective
+        if log:
+            self._log("Discriminator", {"discriminator_adv_loss": d_loss, "disc_weight": disc_weight,
+                                        "logits_real": real.detach().mean(), "logits_fake": fake.detach().mean()},
+                      log if log is not True else None, global_step)
+        return d_loss
+
     def forward(self, codebook_loss, sem_loss, detail_loss, dependency_loss, inputs, reconstructions, optimizer_idx,
                 global_step, last_layer=None, logger=None, log_every=100, fade_blur_schedule=0):
+        if optimizer_idx not in (0, 1):
+            raise ValueError(f"optimizer_idx must be 0 (generator) or 1 (discriminator), got {optimizer_idx}")
         disc_weight = adopt_weight(self.disc_weight, global_step, threshold=self.discriminator_iter_start)
-        log_now = logger is not None and global_step % log_every == 0
-        if optimizer_idx == 0:                          # ---- generator update (:153-207)
-            rec_loss = self.rec_loss(inputs.contiguous(), reconstructions.contiguous())
-            p_loss = torch.mean(self.perceptual_loss(inputs.contiguous(), reconstructions.contiguous()))
-            logits_fake = self.discriminator(self._disc_in(reconstructions.contiguous(), fade_blur_schedule))
-            generator_adv_loss = self.gen_adv_loss(logits_fake)
-            if self.disc_adaptive_weight:
-                null_loss = self.rec_weight * rec_loss + self.perceptual_weight * p_loss
-                adaptive = self.calculate_adaptive_weight(null_loss, generator_adv_loss, last_layer=last_layer)
-            else:
-                adaptive = 1
-            sem_loss = 0 if sem_loss is None else sem_loss
-            detail_loss = 0 if detail_loss is None else detail_loss
-            dependency_loss = 0 if dependency_loss is None else dependency_loss
-            loss = self.rec_weight * rec_loss + self.perceptual_weight * p_loss + \
-                adaptive * disc_weight * generator_adv_loss + \
-                codebook_loss[0] + codebook_loss[1] + codebook_loss[2] + sem_loss + detail_loss + dependency_loss
-            if log_now or (self.wandb_tracker is not None and global_step % log_every == 0):
-                stats = {"rec_loss": self.rec_weight * rec_loss, "perceptual_loss": self.perceptual_weight * p_loss,
-                         "sem_loss": sem_loss, "detail_loss": detail_loss, "dependency_loss": dependency_loss,
-                         "vq_loss": codebook_loss[0], "commit_loss": codebook_loss[1], "entropy_loss": codebook_loss[2],
-                         "generator_adv_loss": adaptive * disc_weight * generator_adv_loss,
-                         "disc_adaptive_weight": adaptive, "disc_weight": disc_weight}
-                stats = {k: float(v) for k, v in stats.items()}
-                if log_now:
-                    logger.info("(Generator) " + ", ".join(f"{k}: {v:.4f}" for k, v in stats.items())
-                                + f", codebook_usage: {codebook_loss[3]}")
-                if self.wandb_tracker is not None:
-                    usage = codebook_loss[3]
-                    usage = [float(u) for u in usage] if isinstance(usage, (list, tuple)) else float(usage)
-                    self.wandb_tracker.log(dict(stats, codebook_usage=float(np.mean(usage))), step=global_step)
-            return loss
-        if optimizer_idx == 1:                          # ---- discriminator update (:210-247)
-            logits_fake = self.discriminator(self._disc_in(reconstructions.contiguous().detach(), fade_blur_schedule))
-            logits_real = self.discriminator(self._disc_in(inputs.contiguous().detach(), fade_blur_schedule))
-            if self.lecam_loss_weight is not None:
-                self.lecam_ema.update(logits_real, logits_fake)
-                lecam_loss = lecam_reg(logits_real, logits_fake, self.lecam_ema)
-                d_adversarial_loss = disc_weight * (lecam_loss * self.lecam_loss_weight + self.disc_loss(logits_real, logits_fake))
-            else:
-                d_adversarial_loss = disc_weight * self.disc_loss(logits_real, logits_fake)
-            if log_now or (self.wandb_tracker is not None and global_step % log_every == 0):
-                stats = {"discriminator_adv_loss": float(d_adversarial_loss), "disc_weight": float(disc_weight),
-                         "logits_real": float(logits_real.detach().mean()), "logits_fake": float(logits_fake.detach().mean())}
-                if log_now:
-                    logger.info("(Discriminator) " + ", ".join(f"{k}: {v:.4f}" for k, v in stats.items()))
-                if self.wandb_tracker is not None:
-                    self.wandb_tracker.log(stats, step=global_step)
-            return d_adversarial_loss
-        raise ValueError(f"optimizer_idx must be 0 (generator) or 1 (discriminator), got {optimizer_idx}")
+        due = global_step % log_every == 0
+        log = (logger if logger is not None else True) if (due and (logger is not None or self.wandb_tracker is not None)) else False
+        x, y = inputs.contiguous(), reconstructions.contiguous()
+        if optimizer_idx == 0:
+            return self._generator_step(codebook_loss, (sem_loss, detail_loss, dependency_loss), x, y, global_step, last_layer,
+                                        disc_weight, fade_blur_schedule, log)
+        return self._discriminator_step(x, y, global_step, disc_weight, fade_blur_schedule, log)
