@@ -106,6 +106,62 @@ class PatchGANDiscriminator(nn.Module):
         return self.main(input)
 
 
+class _Blur3(nn.Module):
+    """[1,2,1] x [1,2,1] / 16 binomial blur per channel with reflect padding (what kornia.filters.filter2d(x, f,
+    normalized=True) computes in discriminator_stylegan.py:86-95); buffer name `f` as in the reference."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer('f', torch.tensor([1., 2., 1.]))
+
+    def forward(self, x):
+        k = self.f[None, :] * self.f[:, None]
+        k = (k / k.sum()).to(x.dtype)[None, None].expand(x.shape[1], 1, 3, 3)
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), k, groups=x.shape[1])
+
+
+class _StyleGANBlock(nn.Module):
+    """residual down-block: 1x1 stride-2 skip + (3x3, 3x3, blur, 3x3 stride-2), summed and scaled by 1/sqrt2 (:58-82)"""
+
+    def __init__(self, input_channels, filters, downsample=True):
+        super().__init__()
+        act = lambda: nn.LeakyReLU(0.2, inplace=True)
+        self.conv_res = nn.Conv2d(input_channels, filters, 1, stride=2 if downsample else 1)
+        self.net = nn.Sequential(nn.Conv2d(input_channels, filters, 3, padding=1), act(),
+                                 nn.Conv2d(filters, filters, 3, padding=1), act())
+        self.downsample = nn.Sequential(_Blur3(), nn.Conv2d(filters, filters, 3, padding=1, stride=2)) if downsample else None
+
+    def forward(self, x):
+        y = self.net(x)
+        if self.downsample is not None:
+            y = self.downsample(y)
+        return (y + self.conv_res(x)) * (1 / np.sqrt(2))
+
+
+class StyleGANDiscriminator(nn.Module):
+    """StyleGAN2-style residual discriminator down to 4x4 + 2-layer MLP (discriminator_stylegan.py:13-55); keys
+    `blocks.{i}...`, `final_conv.0`, `final_linear.{0,2}`."""
+
+    def __init__(self, input_nc=3, ndf=64, n_layers=3, channel_multiplier=1, image_size=256):
+        super().__init__()
+        width = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * channel_multiplier, 128: 128 * channel_multiplier,
+                 256: 64 * channel_multiplier, 512: 32 * channel_multiplier, 1024: 16 * channel_multiplier}
+        stages = int(np.log2(image_size))
+        cin = width[image_size]
+        blocks = [nn.Conv2d(input_nc, cin, 3, padding=1), nn.LeakyReLU(0.2, inplace=True)]
+        for i in range(stages, 2, -1):
+            blocks.append(_StyleGANBlock(cin, width[2 ** (i - 1)]))
+            cin = width[2 ** (i - 1)]
+        self.blocks = nn.ModuleList(blocks)
+        self.final_conv = nn.Sequential(nn.Conv2d(cin, width[4], 3, padding=1), nn.LeakyReLU(0.2, inplace=True))
+        self.final_linear = nn.Sequential(nn.Linear(width[4] * 16, width[4]), nn.LeakyReLU(0.2, inplace=True), nn.Linear(width[4], 1))
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = blk(x)
+        return self.final_linear(self.final_conv(x).flatten(1))
+
+
 class VQLoss(nn.Module):
     def __init__(self, disc_start, disc_loss="hinge", disc_dim=64, disc_type='patchgan', image_size=256,
                  disc_num_layers=3, disc_in_channels=3, disc_weight=1.0, disc_adaptive_weight=False,
@@ -119,11 +175,13 @@ class VQLoss(nn.Module):
         self.disc_type = disc_type
         if disc_type == "patchgan":
             self.discriminator = PatchGANDiscriminator(input_nc=disc_in_channels, n_layers=disc_num_layers, ndf=disc_dim)
+        elif disc_type == "stylegan":
+            self.discriminator = StyleGANDiscriminator(input_nc=disc_in_channels, image_size=image_size)
         elif disc_type == "dinodisc":
             self.discriminator = DINODiscriminator(norm_type=norm_type)
             self.daug = DiffAug(prob=aug_prob, cutout=0.2)
         else:
-            raise NotImplementedError(f"disc_type={disc_type!r}: no shipped config selects it (all use 'dinodisc'); not built")
+            raise NotImplementedError("disc_type='samdisc' names a class the reference never defines (vq_loss.py:107)")
         self.disc_loss = {"hinge": hinge_d_loss, "vanilla": vanilla_d_loss, "non-saturating": non_saturating_d_loss}[disc_loss]
         self.discriminator_iter_start = disc_start
         self.disc_weight = disc_weight

@@ -328,6 +328,10 @@ def case_loss_stack():
     pg = NLayerDiscriminator(input_nc=3, n_layers=3, ndf=16)
     d["patchgan_keys"] = np.array(sorted(pg.state_dict().keys()))
     d["patchgan_shapes"] = np.array([str(tuple(v.shape)) for k, v in sorted(pg.state_dict().items())])
+    from tokenizer.tokenizer_image.discriminator_stylegan import Discriminator as SGD
+    sg = SGD(input_nc=3, image_size=32)
+    d["stylegan_keys"] = np.array(sorted(sg.state_dict().keys()))
+    d["stylegan_shapes"] = np.array([str(tuple(v.shape)) for k, v in sorted(sg.state_dict().items())])
     np.savez_compressed(os.path.join(OUT, "loss_stack.npz"), **d)
     print("loss_stack: aug cases", len(cases), "lpips keys", len(d["lpips_keys"]), "dino acts", len(acts))
 

@@ -120,6 +120,28 @@ def test_patchgan_layout_and_vqloss_patchgan_on_cpu():
     with pytest.raises(ValueError):
         loss(cb, None, None, None, x, rec, 2, 0)
     with pytest.raises(NotImplementedError):
-        VQLoss(disc_start=0, disc_type='stylegan')
+        VQLoss(disc_start=0, disc_type='samdisc')
     with pytest.raises(AssertionError):
         VQLoss(disc_start=0, disc_loss='wgan')
+
+
+def test_stylegan_discriminator_layout_and_blur():
+    from imagefolder_b200.vq_loss import StyleGANDiscriminator, VQLoss, _Blur3
+    g = load_golden("loss_stack")
+    m = StyleGANDiscriminator(input_nc=3, image_size=32)
+    assert sorted(m.state_dict().keys()) == list(g["stylegan_keys"])
+    assert [str(tuple(v.shape)) for _, v in sorted(m.state_dict().items())] == list(g["stylegan_shapes"])
+    assert m(torch.randn(2, 3, 32, 32)).shape == (2, 1)
+    # the blur is the normalised [1,2,1]x[1,2,1] filter with reflect borders (kornia filter2d semantics; kornia itself is
+    # not installed here, so this is checked against a direct evaluation, not against the reference)
+    x = torch.arange(2 * 2 * 5 * 5, dtype=torch.float32).reshape(2, 2, 5, 5)
+    y = _Blur3()(x)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1), mode='reflect')
+    k = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]]) / 16
+    want = sum(k[i, j] * xp[:, :, i:i + 5, j:j + 5] for i in range(3) for j in range(3))
+    close(y, want, rtol=1e-6, atol=1e-6)
+    close(_Blur3()(torch.ones(1, 3, 8, 8)), torch.ones(1, 3, 8, 8))         # normalised: constants are preserved
+    loss = VQLoss(disc_start=0, disc_type='stylegan', image_size=32)
+    x = torch.rand(2, 3, 32, 32) * 2 - 1
+    cb = (torch.tensor(0.1), torch.tensor(0.1), torch.tensor(0.0), [1.0])
+    assert torch.isfinite(loss(cb, None, None, None, x, x * 0.9, 0, 1)) and torch.isfinite(loss(cb, None, None, None, x, x * 0.9, 1, 1))
