@@ -112,3 +112,44 @@ def test_pretokenize_round_trip(name, tmp_path):
         rec = model.decode_tokens(pt.unflatten_codes(toks, model))
         ref = model.img_to_reconstructed_img(torch.cat([x, torch.flip(x, dims=[-1])]).cuda())
     np.testing.assert_allclose(npy(rec), npy(ref), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["VQ-8192", "MSVR10P2-4096"])
+def test_full_training_iteration_with_loss_stack(name):
+    """one iteration exactly as xqgan_train.py:448-470 wires it: tokenizer forward -> VQLoss generator branch (L2 + LPIPS +
+    adaptive-weighted adversarial term through DiffAug + DINO discriminator) -> optimizer; then the discriminator branch ->
+    its optimizer.  Random LPIPS / DINO weights (no network), so only the plumbing and the gradients are checked."""
+    import warnings
+    from imagefolder_b200.vq_loss import VQLoss
+    warnings.filterwarnings("ignore", message=".*RANDOM.*")
+    model, args = small_model(name)
+    model = model.cuda().train()
+    torch.manual_seed(1)
+    vq_loss = VQLoss(disc_start=0, disc_weight=0.5, disc_type='dinodisc', disc_loss='hinge', gen_adv_loss='hinge',
+                     disc_adaptive_weight=True, lecam_loss_weight=0.001, perceptual_weight=1.0, aug_prob=1.0).cuda().train()
+    opt_g = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    opt_d = torch.optim.AdamW(vq_loss.discriminator.parameters(), lr=1e-4, fused=True)
+    x = (torch.rand(4, 3, 256, 256) * 2 - 1).cuda()
+    head_before = [p.detach().clone() for p in vq_loss.discriminator.heads.parameters()]
+    enc_before = model.encoder.latent_tokens.detach().clone()
+    for step in range(2):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            recons, codebook_loss, sem_loss, detail_loss, dependency_loss = model(x, 0, 0.0, 0.0, 100)
+            loss_gen = vq_loss(codebook_loss, sem_loss, detail_loss, dependency_loss, x, recons, optimizer_idx=0,
+                               global_step=step + 1, last_layer=model.decoder.last_layer, fade_blur_schedule=0)
+        assert torch.isfinite(loss_gen)
+        opt_g.zero_grad(set_to_none=True)
+        loss_gen.backward()
+        assert all(p.grad is None for p in vq_loss.perceptual_loss.parameters())          # LPIPS is frozen
+        assert torch.isfinite(model.decoder.last_layer.grad).all()
+        opt_g.step()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss_disc = vq_loss(codebook_loss, sem_loss, detail_loss, dependency_loss, x, recons, optimizer_idx=1,
+                                global_step=step + 1, fade_blur_schedule=0)
+        assert torch.isfinite(loss_disc)
+        opt_d.zero_grad(set_to_none=True)
+        loss_disc.backward()
+        opt_d.step()
+    assert not torch.equal(enc_before, model.encoder.latent_tokens.detach())
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(head_before, vq_loss.discriminator.heads.parameters()))
+    assert not any(p.requires_grad for p in vq_loss.discriminator.dino_proxy[0].parameters())   # frozen backbone
