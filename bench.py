@@ -102,6 +102,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def top_kernel_roofline(kern_table, hbm_peak, step_ms, ncu_traffic=None):
+    """HBM roofline of the libxqb200 entry point that takes the most time per step (the VQ search kernel that BASELINE's metric
+    names is two orders of magnitude smaller than the ViT glue kernels)."""
+    rows = [r for r in kern_table if r.get("alg_GBps")]
+    if not rows:
+        return None
+    top = max(rows, key=lambda r: r["ms_per_step"])
+    return {"bound": "hbm", "kernel": top["entry"], "achieved": top["alg_GBps"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": top["alg_GBps"] / hbm_peak, "traffic": (ncu_traffic or {}).get(top["entry"]),
+            "ms_per_call": top["ms_per_call"], "calls_per_step": top["calls_per_step"],
+            "share_of_step": top["ms_per_step"] / step_ms if step_ms else None,
+            "note": "algorithmic bytes (each call's operands once) / CUDA-event time of the call inside the timed steps, "
+                    "launch gaps and helper launches (memset, partial reduce) included; traffic = dram bytes of one launch "
+                    "from the ncu capture in profiles/ (B = 256 shapes)"}
+
+
+def _safe(fn):
+    try:
+        return fn()
+    except Exception as e:          # an explanatory extra must never cost the bench line
+        return {"error": repr(e)[:200]}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -290,6 +313,9 @@ def run_ours(a):
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "peak_mem_gib": peak_mem,
         "our_kernels": [dict(r, hbm_frac=(r["alg_GBps"] / hbm if r["alg_GBps"] else None)) for r in kern_table],
         "our_kernels_ms_per_step": sum(r["ms_per_step"] for r in kern_table),
+        "roofline_top_kernel": _safe(lambda: top_kernel_roofline(
+            kern_table, hbm, ms / a.steps,
+            {"xq_vit_residual_ln_bwd": 1.788e9} if (a.workload == "VQ-8192" and B == 256) else None)),
         "last_loss": loss_host,
     }
     if not a.no_cpu_baseline and world == 1 and a.impl == "ours":
