@@ -75,3 +75,21 @@ def test_state_dict_keys_match_reference():
     assert q._phi_map(10) == [0, 0, 1, 1, 1, 2, 2, 3, 3, 3]        # SURVEY.md 8a / quant.py:285-288
     assert VectorQuantizer2(8, 4, v_patch_nums=pn, share_quant_resi=1)._phi_map(3) == [0, 0, 0]
     assert VectorQuantizer2(8, 4, v_patch_nums=pn, share_quant_resi=0)._phi_map(3) == [0, 1, 2]
+
+
+def test_bench_helpers_are_total():
+    """bench.py's explanatory extras must never cost the JSON line (no GPU needed for these helpers)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    rows = [{"entry": "xq_vit_residual_ln_bwd", "calls_per_step": 50.0, "ms_per_step": 16.7, "ms_per_call": 0.334, "alg_GBps": 5350.0},
+            {"entry": "xq_vq_forward", "calls_per_step": 1.0, "ms_per_step": 0.2, "ms_per_call": 0.2, "alg_GBps": None}]
+    r = b.top_kernel_roofline(rows, 6385.8, 211.0, {"xq_vit_residual_ln_bwd": 1.788e9})
+    assert r["kernel"] == "xq_vit_residual_ln_bwd" and r["bound"] == "hbm" and abs(r["frac"] - 5350.0 / 6385.8) < 1e-12
+    assert r["traffic"] == 1.788e9 and abs(r["share_of_step"] - 16.7 / 211.0) < 1e-12
+    assert b.top_kernel_roofline([], 6385.8, 1.0) is None
+    assert b.top_kernel_roofline(rows[1:], 6385.8, 1.0) is None
+    assert "error" in b._safe(lambda: 1 / 0) and b._safe(lambda: 3) == 3
+    hbm, tf, src = b.peaks()
+    assert hbm > 1000 and tf > 100 and src in ("measured", "fallback")
