@@ -6,7 +6,7 @@ Appendix A (hand-written backward kernels), not autograd traces.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

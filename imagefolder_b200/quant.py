@@ -14,7 +14,6 @@ Differences from the reference, all host-side:
 """
 from __future__ import annotations
 
-from math import sqrt
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np

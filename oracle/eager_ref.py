@@ -14,8 +14,6 @@ Follows: VectorQuantizer.forward            tokenizer/tokenizer_image/xqgan_mode
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn.functional as F
 
