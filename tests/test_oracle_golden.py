@@ -137,3 +137,34 @@ def test_var_feature_map_helpers(name):
         close(nxt, g[f"next{si}"])
     close(F, g["ar_f_hat"])
     np.testing.assert_array_equal(F, fl[-1])          # the AR chain and embed_to_fhat are the same arithmetic
+
+
+def test_oracle_edge_cases_ties_and_degenerate_sizes():
+    """first-index tie-break, single row / single code / single channel, zero rows (the normalisation clamp) --
+    the conventions the CUDA kernels are held to."""
+    rng = np.random.default_rng(0)
+    # duplicated codes: the FIRST of the equal codes wins, for both metrics
+    codes = rng.standard_normal((6, 5)).astype(np.float32)
+    codes[4] = codes[1]
+    rows = np.stack([codes[1], codes[4] * 1.0, codes[3]]).astype(np.float32)
+    for metric in (0, 1):
+        idx, best, second = xo.search(rows, codes if metric == 0 else xo.l2norm_rows(codes)[0], metric)
+        assert list(idx) == [1, 1, 3]
+    # V = 1, N = 1, C = 1
+    idx, _, _ = xo.search(np.array([[2.0]], np.float32), np.array([[-1.0]], np.float32), 0)
+    assert list(idx) == [0]
+    # an all-zero row normalises to zero (den clamped to 1e-12) and still gets a valid index
+    y, den = xo.l2norm_rows(np.zeros((2, 4), np.float32))
+    assert np.all(y == 0) and np.allclose(den, 1e-12)
+    fwd = xo.vq_forward(np.zeros((1, 4, 2, 2), np.float32), rng.standard_normal((7, 4)).astype(np.float32))
+    assert fwd["idx"].shape == (4,) and np.all((fwd["idx"] >= 0) & (fwd["idx"] < 7)) and np.isfinite(fwd["out"]).all()
+    # rank_select with delta > number of distinct distances: ranks follow (distance, index) order
+    codes = np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]], np.float32)
+    r = np.array([[1.0, 0.0]], np.float32)
+    out, topk = xo.rank_select(r, codes, np.array([1]), 3, want_topk=True)
+    assert list(topk[0]) == [0, 1, 2] and list(out) == [1]
+    # area pool P = H is the identity, P = 1 the global mean; bicubic P = H is the identity
+    f = rng.standard_normal((2, 3, 5, 5)).astype(np.float32)
+    np.testing.assert_array_equal(xo.rows_to_nchw(xo.area_pool_rows(f, 5), f.shape), f)
+    np.testing.assert_allclose(xo.area_pool_rows(f, 1).reshape(2, 3), f.reshape(2, 3, -1).mean(-1), rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(xo.bicubic_up(xo.nchw_to_rows(f), 2, 3, 5, 5, 5), f)
