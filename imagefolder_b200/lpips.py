@@ -6,6 +6,11 @@ reference does AFTER the trunk -- per stage: channel-normalise both maps, subtra
 i.e. ~10 full passes over feature maps of up to 2 GB -- is one fused CUDA pass per stage (xq_lpips_layer_forward /
 _backward, csrc/loss_kernels.cu).
 
+On CUDA tensors the stage distance ALWAYS goes through libxqb200 (and fails loudly if the library is missing); there is no
+silent substitute.  Two situations keep the reference's op sequence on library kernels by design: train-mode dropout in
+front of the `lin` conv (a semantic the fused kernel does not have; `VQLoss` keeps LPIPS in eval mode), and CPU tensors,
+where the whole module -- trunk included -- is a plain library network.
+
 There is no network here: `load_from_pretrained` reads `<this dir>/cache/vgg.pth` (the reference's cache location,
 lpips.py:67-69) or `$XQ_LPIPS_CKPT` when present and otherwise leaves the random initialisation in place with a warning.
 """
