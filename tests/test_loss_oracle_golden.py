@@ -52,3 +52,36 @@ def test_gan_losses_and_schedules():
 def test_batchnorm_local():
     g = load_golden("loss_stack")
     close(lo.batchnorm_local(g["bnl_x"], g["bnl_w"], g["bnl_b"], virtual_bs=4), g["bnl_y"], rtol=1e-5, atol=1e-5)
+
+
+def test_loss_oracle_properties():
+    """size-independent properties of the restatements themselves: DiffAug backward is the transpose of its affine forward,
+    the LPIPS stage distance is symmetric, non-negative, zero on identical maps, and its analytic gradient matches finite
+    differences."""
+    rng = np.random.default_rng(0)
+    for flags in [(1, 1, 1), (1, 0, 1), (0, 1, 0), (0, 0, 1)]:
+        B, C, H, W = 3, 3, 12, 10
+        r = rng.random((7, B)).astype(np.float32)
+        x, g = rng.standard_normal((B, C, H, W)).astype(np.float32), rng.standard_normal((B, C, H, W)).astype(np.float32)
+        y = lo.diffaug_forward(x, flags, r).astype(np.float64)
+        y0 = lo.diffaug_forward(np.zeros_like(x), flags, r).astype(np.float64)
+        lhs = ((y - y0) * g).sum()
+        rhs = (x.astype(np.float64) * lo.diffaug_backward(g, flags, r)).sum()
+        assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+    f0 = np.maximum(rng.standard_normal((2, 16, 4, 5)), 0)
+    f1 = np.maximum(rng.standard_normal((2, 16, 4, 5)), 0)
+    w = rng.random(16) * 0.2
+    v01, v10 = lo.lpips_stage(f0, f1, w), lo.lpips_stage(f1, f0, w)
+    close(v01, v10, rtol=1e-12, atol=0)
+    assert np.all(v01 >= 0) and np.all(lo.lpips_stage(f0, f0, w) < 1e-20)
+    gvec = rng.standard_normal(2)
+    grad = lo.lpips_stage_backward(f0, f1, w, gvec)
+    eps = 1e-6
+    for (b, c, h, ww) in [(0, 3, 1, 2), (1, 7, 0, 4), (0, 15, 3, 0)]:
+        if f1[b, c, h, ww] == 0:
+            continue                              # post-ReLU zero: one-sided
+        fp, fm = f1.copy(), f1.copy()
+        fp[b, c, h, ww] += eps
+        fm[b, c, h, ww] -= eps
+        num = ((lo.lpips_stage(f0, fp, w) - lo.lpips_stage(f0, fm, w)) * gvec).sum() / (2 * eps)
+        assert abs(num - grad[b, c, h, ww]) <= 1e-5 * max(1e-3, abs(num))
