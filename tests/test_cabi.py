@@ -93,3 +93,35 @@ def test_bench_helpers_are_total():
     assert "error" in b._safe(lambda: 1 / 0) and b._safe(lambda: 3) == 3
     hbm, tf, src = b.peaks()
     assert hbm > 1000 and tf > 100 and src in ("measured", "fallback")
+
+
+def test_argument_validation_of_the_newer_entry_points_without_gpu():
+    """every check below fails BEFORE any CUDA call, so it runs without a device"""
+    import ctypes as C
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    one = C.c_void_p(16)                     # a non-null dummy pointer; never dereferenced on these paths
+    d = _capi.make_ms_desc(2, 8, 5, 5, 64, 4, [1, 2, 5], [0, 1, 3], _capi.XQ_MS_VQ_ZNORM)
+    f = C.cast(one, C.POINTER(C.c_float))
+    assert L.xq_ms_embed(d, 0, 4, f, f, f, None, f, None, None, None) == -1           # si1 > SN
+    assert L.xq_ms_embed(d, 2, 2, f, f, f, None, f, None, None, None) == -1           # empty range
+    assert L.xq_ms_embed(d, 0, 3, None, f, f, None, f, None, None, None) == -1        # no feature maps
+    assert L.xq_lpips_workspace_bytes(4, 64 * 64) >= 8 * 4 * 16
+    assert L.xq_lpips_layer_forward(None, one, 0, f, 1, 8, 16, 1e-10, 0, f, one, 1 << 20, None) == -1
+    assert L.xq_lpips_layer_forward(one, one, 0, f, 2, 8, 4096, 1e-10, 0, f, one, 8, None) == -2     # workspace too small
+    assert L.xq_lpips_layer_forward(one, one, 1, f, 1, 8, 15, 1e-10, 0, f, one, 1 << 20, None) == -4  # bf16 needs even H*W
+    assert L.xq_lpips_layer_backward(one, one, 0, f, 0, 8, 16, 1e-10, f, one, None) == -1
+    assert L.xq_diffaug_forward(f, f, 2, 9, 8, 8, 7, 2, 2, f, f, None) == -4          # more than 8 channels
+    assert L.xq_diffaug_forward(f, None, 2, 3, 8, 8, 1, 2, 2, f, f, None) == -1       # flags set but no random numbers
+    assert L.xq_diffaug_backward(f, f, 2, 3, 8, 8, 8, 2, 2, f, f, None) == -1         # unknown flag bit
+    assert L.xq_vit_pack_workspace_bytes() >= 4
+    assert L.xq_vit_pack_qkv(one, one, one, one, None, 16, 768, one, 2, None) == -2    # workspace too small
+    assert L.xq_vit_pack_qkv(one, one, one, one, None, 16, 4096, one, 256, None) == -4  # 3C/8 chunks beyond the kernel's range
+    assert L.xq_vit_pack_qkv(one, one, one, one, None, 16, 12, one, 256, None) == -1   # C % 8 != 0
+    assert L.xq_vit_assemble_fwd(one, 1, f, 2, 4, 6, 16, 3, f, None) == -1            # t0 + Ls > T
+    assert L.xq_vit_assemble_fwd(one, 1, f, 2, 4, 8, 18, 1, f, None) == -1            # D % 4 != 0
+    assert L.xq_vit_assemble_bwd(f, 2, 4, 8, 16, 1, None, 0, None, None) == -1        # nothing to compute
+    assert L.xq_vit_patchify(f, one, 2, 3, 64, 64, 6, None) == -4                      # patch % 4 != 0
+    assert L.xq_vit_patchify(f, one, 2, 3, 60, 64, 16, None) == -4                     # H % patch != 0
+    assert L.xq_vit_residual_ln_bwd(None, None, None, None, None, None, None, None, None, None, 1, 8, 768, None, None, None,
+                                    None, None, None, None, 0, None) == -1
