@@ -233,6 +233,15 @@ int xq_vit_gelu_fwd(const void *x, const float *bias, void *y, int M, int C, voi
 int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *g_bias, int M, int C,
                     void *stream);
 
+/*   Flash attention of the ViT blocks, head_dim 64, no mask, no dropout (Attention.forward,
+ *   tokenizer/tokenizer_image/dino_enc/vision_transformer.py:173-197: F.scaled_dot_product_attention on
+ *   qkv.reshape(B,N,3,H,hd).permute(2,0,3,1,4), then x.transpose(1,2).reshape(B,N,C)).  tcgen05 / TMEM / TMA kernel.
+ *     qkv   bf16 [B,N,3,H,64]  the packed projection, read in place (no q/k/v copies)
+ *     out   bf16 [B,N,H*64]    head-merged attention output (what `proj` consumes)
+ *     lse2  fp32 [B,H,N]       base-2 log-sum-exp of the scaled scores (scale*log2(e)*q.k), saved for backward
+ *   scale = head_dim^-0.5 (Attention.scale).  Any N >= 1; qkv / out 16-byte aligned. */
+int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H, int head_dim, float scale, void *stream);
+
 /*
  * ---- loss stack -------------------------------------------------------------------
  * LPIPS stage distance (tokenizer/tokenizer_image/lpips.py:79-90): for one VGG stage with feature maps f0, f1
