@@ -286,6 +286,482 @@ static bool get_fwd_maps(const void *qkv, void *out, int B, int N, int H, AttnMa
     return true;
 }
 
+
+// =====================================================================================================================
+// Backward.  One CTA per (batch, head, 128-key block), 1 CTA per SM, looping over the query blocks i:
+//     S^T  = K Q_i^T              (M = keys on TMEM lanes, N = queries)            TMEM [0,128)
+//     dP^T = V dO_i^T                                                              TMEM [128,256)
+//     P^T  = exp2(S^T c - L2[q])            -> bf16 -> TMEM [448,512)
+//     dS^T = P^T o (dP^T - delta[q])        -> bf16 -> TMEM (over dP^T) and, transposed view, smem (MN-major A operand)
+//     dV  += P^T dO_i   (A from TMEM, B = dO tile MN-major)                        TMEM [256,320)
+//     dK  += dS^T Q_i   (A from TMEM, B = Q tile MN-major)                         TMEM [320,384)
+//     dQ_i = dS K       (A = dS smem MN-major, B = K tile MN-major)                TMEM [384,448) -> fp32 smem -> TMA reduce-add
+// With keys on the lanes, the softmax statistics L2[q] / delta[q] are per COLUMN: broadcast reads from shared memory.
+// The query tail is cheap (it is the MMA N / K extent, rounded to 16); `scale` is folded into the dK epilogue and the
+// dQ conversion.  dQ is accumulated across the key blocks of a (batch, head) in an fp32 workspace by TMA reduce-add
+// and converted to bf16 into dqkv by attn_dq_convert_kernel.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 4-11 = compute (warp % 4 = TMEM lane quarter, (warp-4)/4 = query half).
+// =====================================================================================================================
+constexpr int AB_THREADS = 384;
+
+struct AttnBwdSmem {
+    static constexpr int K = 0;
+    static constexpr int V = AT_TILE;
+    static constexpr int Q = 2 * AT_TILE;           // 2 stages
+    static constexpr int DO = 4 * AT_TILE;          // 2 stages
+    static constexpr int DS = 6 * AT_TILE;          // 2 stages x 2 row tiles
+    static constexpr int DQ = 10 * AT_TILE;         // fp32 staging: 2 row tiles [128][32 fp32]
+    static constexpr int STAT = 12 * AT_TILE;       // lse[2][128], delta[2][128]
+    static constexpr int BAR = STAT + 2048;
+    static constexpr int BYTES = BAR + 256;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmDQ,
+                const float *__restrict__ lseP, const float *__restrict__ deltaP, int N, int H, int nK, int Npad, float c,
+                float scale) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
+    uint64_t *kv_full = bars + 0;
+    uint64_t *q_full = bars + 1;      // [2]
+    uint64_t *q_empty = bars + 3;     // [2]
+    uint64_t *s_full = bars + 5;
+    uint64_t *s_free = bars + 6;
+    uint64_t *dp_full = bars + 7;
+    uint64_t *p_full = bars + 8;
+    uint64_t *dv_done = bars + 9;
+    uint64_t *ds_full = bars + 10;
+    uint64_t *dq_full = bars + 11;
+    uint64_t *dq_free = bars + 12;
+    uint64_t *dkv_done = bars + 13;
+    uint32_t *tmem_holder = (uint32_t *)(bars + 14);
+    float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [2][128]
+    float *s_delta = s_lse + 256;                                // [2][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bh = blockIdx.x / nK, jb = blockIdx.x - bh * nK;
+    const int b = bh / H, h = bh - b * H;
+    const int k0 = jb * AT_BN;
+    const int nQ = Npad / AT_BM;
+    const int colQ = h * AT_D, colK = (H + h) * AT_D, colV = (2 * H + h) * AT_D;
+
+    if (tid == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 8);
+        mbar_init(dp_full, 1);
+        mbar_init(p_full, 8);
+        mbar_init(dv_done, 1);
+        mbar_init(ds_full, 8);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_free, 8);
+        mbar_init(dkv_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+    const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tP = tmem + 448;
+
+    if (warp < 4) {
+        reg_dec<88>();
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer =====
+            tma_prefetch_desc(&tmQKV);
+            tma_prefetch_desc(&tmDO);
+            mbar_expect_tx(kv_full, 2 * AT_TILE);
+            tma_load_3d(base + AttnBwdSmem::K, &tmQKV, colK, k0, b, kv_full);
+            tma_load_3d(base + AttnBwdSmem::V, &tmQKV, colV, k0, b, kv_full);
+            for (int i = 0; i < nQ; ++i) {
+                const int st = i & 1;
+                mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&q_full[st], 2 * AT_TILE + 1024);
+                tma_load_3d(base + AttnBwdSmem::Q + st * AT_TILE, &tmQKV, colQ, i * AT_BM, b, &q_full[st]);
+                tma_load_3d(base + AttnBwdSmem::DO + st * AT_TILE, &tmDO, h * AT_D, i * AT_BM, b, &q_full[st]);
+                bulk_load_1d(s_lse + st * 128, lseP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+                bulk_load_1d(s_delta + st * 128, deltaP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t ka = smem_u32(base + AttnBwdSmem::K), va = smem_u32(base + AttnBwdSmem::V);
+            auto nqr_of = [&](int i) { return (min(AT_BM, N - i * AT_BM) + 15) & ~15; };
+            auto issue_s = [&](int i) {
+                const uint32_t qa = smem_u32(base + AttnBwdSmem::Q + (i & 1) * AT_TILE);
+                const uint32_t id = idesc_bf16(AT_BN, nqr_of(i), 0, 0);
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_k_sw128(ka + k * 32), desc_k_sw128(qa + k * 32), id, k > 0);
+                umma_commit(s_full);
+            };
+            auto issue_dp = [&](int i) {
+                const uint32_t da = smem_u32(base + AttnBwdSmem::DO + (i & 1) * AT_TILE);
+                const uint32_t id = idesc_bf16(AT_BN, nqr_of(i), 0, 0);
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_k_sw128(va + k * 32), desc_k_sw128(da + k * 32), id, k > 0);
+                umma_commit(dp_full);
+            };
+            mbar_wait(kv_full, 0);
+            mbar_wait(&q_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            issue_dp(0);
+            const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
+            const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
+            for (int i = 0; i < nQ; ++i) {
+                const int st = i & 1;
+                const int ks = nqr_of(i) / 16;
+                if (i + 1 < nQ) {
+                    mbar_wait(s_free, i & 1);
+                    mbar_wait(&q_full[st ^ 1], ((i + 1) >> 1) & 1);
+                    tc_fence_after();
+                    issue_s(i + 1);
+                }
+                const uint32_t qa = smem_u32(base + AttnBwdSmem::Q + st * AT_TILE);
+                const uint32_t da = smem_u32(base + AttnBwdSmem::DO + st * AT_TILE);
+                mbar_wait(p_full, i & 1);
+                tc_fence_after();
+                for (int k = 0; k < ks; ++k)       // dV += P^T dO_i : query k-step k lives at P column (k/4)*32 + (k%4)*8
+                    umma_ts(tDV, tP + (k >> 2) * 32 + (k & 3) * 8, desc_mn_sw128(da + k * 2048, 16384, 1024), id_acc, (i | k) != 0);
+                umma_commit(dv_done);
+                mbar_wait(ds_full, i & 1);
+                tc_fence_after();
+                for (int k = 0; k < ks; ++k)       // dK += dS^T Q_i : dS^T (bf16) sits over dP^T at column (k/4)*64 + (k%4)*8
+                    umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_mn_sw128(qa + k * 2048, 16384, 1024), id_acc, (i | k) != 0);
+                umma_commit(&q_empty[st]);         // Q_i / dO_i tiles are dead once dV_i and dK_i retire
+                if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
+                const uint32_t dsa = smem_u32(base + AttnBwdSmem::DS + st * 2 * AT_TILE);
+#pragma unroll
+                for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile [K = keys, N = d]
+                    umma_ss(tDQ, desc_mn_sw128(dsa + k * 2048, AT_TILE, 1024), desc_mn_sw128(ka + k * 2048, 16384, 1024), id_dq, k > 0);
+                umma_commit(dq_full);
+                if (i + 1 < nQ) issue_dp(i + 1);
+            }
+            umma_commit(dkv_done);
+        }
+    } else {
+        reg_inc<208>();
+        // ===== compute: thread = (key lane, query half) =====
+        const int qd = warp & 3;                     // TMEM lane quarter
+        const int hf = (warp - 4) >> 2;              // query half: columns [hf*64, hf*64+64)
+        const int krow = qd * 32 + lane;             // key row inside the block
+        const bool key_ok = k0 + krow < N;
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        const int ctid = tid - 128;                  // 0..255
+        auto drain_dq = [&](int i) {
+            // dQ_i partial (TMEM lanes = queries) -> fp32 smem row tiles -> TMA reduce-add into the accumulator
+            mbar_wait(dq_full, i & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(tDQ + lane_addr + hf * 32, r);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+            if (ctid == 0) bulk_wait_read<0>();      // the previous reduce has finished reading the staging tiles
+            named_bar_sync(2, 256);
+            uint8_t *dst = base + AttnBwdSmem::DQ + hf * AT_TILE;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                *reinterpret_cast<uint4 *>(dst + rowtile_unit(krow, u)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+            fence_async_smem();
+            named_bar_sync(3, 256);
+            if (ctid == 0) {
+                tma_reduce_add_3d(&tmDQ, base + AttnBwdSmem::DQ, 0, i * AT_BM, bh);
+                tma_reduce_add_3d(&tmDQ, base + AttnBwdSmem::DQ + AT_TILE, 32, i * AT_BM, bh);
+                bulk_commit();
+            }
+        };
+        for (int i = 0; i < nQ; ++i) {
+            const int st = i & 1;
+            const int nqr = (min(AT_BM, N - i * AT_BM) + 15) & ~15;
+            const int ncol = max(0, min(64, nqr - hf * 64));        // columns of this half the MMAs produced
+            mbar_wait(&q_full[st], (i >> 1) & 1);                   // statistics of this query block are in smem
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            float p[64];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                if (ch * 16 < ncol) tmem_ld16(tS + lane_addr + hf * 64 + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&p[ch * 16]));
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+            const float4 *l4 = reinterpret_cast<const float4 *>(s_lse + st * 128 + hf * 64);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 L = l4[ch * 4 + g];
+                    const int o = ch * 16 + g * 4;
+                    const bool ok = key_ok && (ch * 16 < ncol);
+                    p[o + 0] = ok ? ex2_approx(fmaf(p[o + 0], c, -L.x)) : 0.f;
+                    p[o + 1] = ok ? ex2_approx(fmaf(p[o + 1], c, -L.y)) : 0.f;
+                    p[o + 2] = ok ? ex2_approx(fmaf(p[o + 2], c, -L.z)) : 0.f;
+                    p[o + 3] = ok ? ex2_approx(fmaf(p[o + 3], c, -L.w)) : 0.f;
+                }
+            }
+            if (i > 0) { mbar_wait(dv_done, (i - 1) & 1); tc_fence_after(); }      // the P buffer is free
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[ch * 32 + 2 * e], p[ch * 32 + 2 * e + 1]);
+                tmem_st16(tP + lane_addr + hf * 32 + ch * 16, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+            if (i > 0) drain_dq(i - 1);
+            mbar_wait(dp_full, i & 1);
+            tc_fence_after();
+            const float4 *d4 = reinterpret_cast<const float4 *>(s_delta + st * 128 + hf * 64);
+            uint8_t *dsrow = base + AttnBwdSmem::DS + st * 2 * AT_TILE + hf * AT_TILE;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t dp[16], pk[8];
+                if (ch * 16 < ncol) {
+                    tmem_ld16(tDP + lane_addr + hf * 64 + ch * 16, dp);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) dp[e] = 0u;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 Dl = d4[ch * 4 + g];
+                    const int o = ch * 16 + g * 4;
+                    const float d0 = p[o + 0] * (__uint_as_float(dp[g * 4 + 0]) - Dl.x);
+                    const float d1 = p[o + 1] * (__uint_as_float(dp[g * 4 + 1]) - Dl.y);
+                    const float d2 = p[o + 2] * (__uint_as_float(dp[g * 4 + 2]) - Dl.z);
+                    const float d3 = p[o + 3] * (__uint_as_float(dp[g * 4 + 3]) - Dl.w);
+                    pk[g * 2 + 0] = pack_bf16(d0, d1);
+                    pk[g * 2 + 1] = pack_bf16(d2, d3);
+                }
+                // dS^T for the dK MMA (TMEM, over this thread's own dP^T columns) ...
+                {
+                    uint32_t lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) lo[e] = pk[e];
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                                 ::"r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]),
+                                   "r"(tDP + lane_addr + hf * 64 + ch * 8)
+                                 : "memory");
+                }
+                // ... and dS for the dQ MMA (smem, MN-major: row = key, 64 queries of this half along the row)
+                *reinterpret_cast<uint4 *>(dsrow + rowtile_unit(krow, ch * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4 *>(dsrow + rowtile_unit(krow, ch * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            fence_async_smem();
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_full);
+        }
+        drain_dq(nQ - 1);
+        // ---- epilogue: dV (query half 0's warps) and dK * scale (half 1's warps) -> bf16 -> smem -> TMA store
+        mbar_wait(dkv_done, 0);
+        tc_fence_after();
+        {
+            const uint32_t src = hf == 0 ? tDV : tDK;
+            const float mul = hf == 0 ? 1.0f : scale;
+            uint8_t *so = base + AttnBwdSmem::Q + hf * AT_TILE;      // both Q stages are dead
+#pragma unroll
+            for (int c0 = 0; c0 < AT_D; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld16(src + lane_addr + c0, o);
+                tmem_wait_ld();
+                uint4 v0, v1;
+                v0.x = pack_bf16(__uint_as_float(o[0]) * mul, __uint_as_float(o[1]) * mul);
+                v0.y = pack_bf16(__uint_as_float(o[2]) * mul, __uint_as_float(o[3]) * mul);
+                v0.z = pack_bf16(__uint_as_float(o[4]) * mul, __uint_as_float(o[5]) * mul);
+                v0.w = pack_bf16(__uint_as_float(o[6]) * mul, __uint_as_float(o[7]) * mul);
+                v1.x = pack_bf16(__uint_as_float(o[8]) * mul, __uint_as_float(o[9]) * mul);
+                v1.y = pack_bf16(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
+                v1.z = pack_bf16(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
+                v1.w = pack_bf16(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
+                *reinterpret_cast<uint4 *>(so + rowtile_unit(krow, c0 / 8)) = v0;
+                *reinterpret_cast<uint4 *>(so + rowtile_unit(krow, c0 / 8 + 1)) = v1;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            named_bar_sync(4 + hf, 128);
+            if ((ctid & 127) == 0) {
+                tma_store_3d(&tmDQKV, so, hf == 0 ? colV : colK, k0, b);
+                bulk_commit();
+            }
+            if (ctid == 0 || ctid == 128) bulk_wait<0>();    // reduce-adds (ctid 0) and stores complete before the CTA retires
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+// delta[bh][n] = sum_d dO * O ; lseP = lse2 re-laid with the row count padded to a multiple of 128 (+inf beyond N, so that
+// padded queries get P = 0) -- both 512-byte-aligned per query block for the bulk copies of attn_bwd_kernel
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ dout,
+                                     const float *__restrict__ lse2, float *__restrict__ lseP, float *__restrict__ deltaP, int B,
+                                     int N, int H, int Npad) {
+    // 8 threads per (b, n, h) row of 64 values (16 bytes each)
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rowid = gid >> 3;
+    const int part = (int)(gid & 7);
+    const long long total = (long long)B * H * Npad;
+    if (rowid >= total) return;
+    const int n = (int)(rowid % Npad);
+    const long long bhh = rowid / Npad;
+    const int hh = (int)(bhh % H);
+    const int bb = (int)(bhh / H);
+    float acc = 0.f;
+    if (n < N) {
+        const size_t off = (((size_t)bb * N + n) * H + hh) * AT_D + part * 8;
+        const uint4 a = *reinterpret_cast<const uint4 *>(out + off);
+        const uint4 g = *reinterpret_cast<const uint4 *>(dout + off);
+        const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&a);
+        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&g);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(a2[e]), y = __bfloat1622float2(g2[e]);
+            acc = fmaf(x.x, y.x, acc);
+            acc = fmaf(x.y, y.y, acc);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (part == 0) {
+        deltaP[rowid] = acc;
+        lseP[rowid] = n < N ? lse2[(size_t)bhh * N + n] : CUDART_INF_F;
+    }
+}
+
+// dq_acc fp32 [B*H][N][64] * scale -> dqkv[b][n][0][h][:] bf16
+__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, __nv_bfloat16 *__restrict__ dqkv, int B, int N, int H,
+                                       float scale) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 8 values
+    const long long total = (long long)B * H * N * 8;
+    if (gid >= total) return;
+    const int part = (int)(gid & 7);
+    const long long rowid = gid >> 3;           // (bh, n)
+    const int n = (int)(rowid % N);
+    const long long bhh = rowid / N;
+    const int hh = (int)(bhh % H);
+    const int bb = (int)(bhh / H);
+    const float4 x0 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
+    const float4 x1 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
+    uint4 o;
+    o.x = pack_bf16(x0.x * scale, x0.y * scale);
+    o.y = pack_bf16(x0.z * scale, x0.w * scale);
+    o.z = pack_bf16(x1.x * scale, x1.y * scale);
+    o.w = pack_bf16(x1.z * scale, x1.w * scale);
+    *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
+}
+
+struct AttnBwdMaps {
+    const void *qkv, *dout, *dqkv, *acc;
+    int B, N, H;
+    CUtensorMap tmQKV, tmDO, tmDQKV, tmDQ;
+};
+
+static bool get_bwd_maps(const void *qkv, const void *dout, void *dqkv, void *acc, int B, int N, int H, AttnBwdMaps &m) {
+    static std::mutex mu;
+    static AttnBwdMaps cache[16];
+    static int n_cached = 0, next = 0;
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].qkv == qkv && cache[i].dout == dout && cache[i].dqkv == dqkv && cache[i].acc == acc && cache[i].B == B &&
+            cache[i].N == N && cache[i].H == H) { m = cache[i]; return true; }
+    AttnBwdMaps e;
+    e.qkv = qkv; e.dout = dout; e.dqkv = dqkv; e.acc = acc; e.B = B; e.N = N; e.H = H;
+    const uint64_t W = (uint64_t)3 * H * AT_D, Wo = (uint64_t)H * AT_D;
+    if (!make_map_3d(&e.tmQKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(qkv), W, N, B, W * 2, (uint64_t)N * W * 2, AT_D, AT_BM)) return false;
+    if (!make_map_3d(&e.tmDQKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dqkv, W, N, B, W * 2, (uint64_t)N * W * 2, AT_D, AT_BM)) return false;
+    if (!make_map_3d(&e.tmDO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(dout), Wo, N, B, Wo * 2, (uint64_t)N * Wo * 2, AT_D, AT_BM)) return false;
+    if (!make_map_3d(&e.tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, acc, AT_D, N, (uint64_t)B * H, AT_D * 4, (uint64_t)N * AT_D * 4, 32, AT_BM)) return false;
+    cache[next] = e;
+    next = (next + 1) % 16;
+    if (n_cached < 16) ++n_cached;
+    m = e;
+    return true;
+}
+
+static size_t attn_bwd_ws_layout(int B, int N, int H, size_t *off_lse, size_t *off_delta) {
+    const size_t Npad = ((size_t)N + AT_BM - 1) / AT_BM * AT_BM;
+    const size_t acc = align_up((size_t)B * H * N * AT_D * sizeof(float), 1024);
+    const size_t st = align_up((size_t)B * H * Npad * sizeof(float), 1024);
+    if (off_lse) *off_lse = acc;
+    if (off_delta) *off_delta = acc + st;
+    return acc + 2 * st;
+}
+
+}  // namespace xq
+
+extern "C" {
+
+size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H) {
+    if (B <= 0 || N <= 0 || H <= 0) return 0;
+    return xq::attn_bwd_ws_layout(B, N, H, nullptr, nullptr);
+}
+
+int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, int B, int N, int H,
+                    int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace xq;
+    if (!qkv || !out || !d_out || !lse2 || !dqkv || !workspace || B <= 0 || N <= 0 || H <= 0) return XQ_ERR_ARG;
+    if (head_dim != AT_D) return XQ_ERR_UNSUPPORTED;
+    if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)d_out & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)workspace & 1023))
+        return XQ_ERR_ARG;
+    size_t off_lse, off_delta;
+    if (workspace_bytes < attn_bwd_ws_layout(B, N, H, &off_lse, &off_delta)) return XQ_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *acc = (float *)workspace;
+    float *lseP = (float *)((char *)workspace + off_lse);
+    float *deltaP = (float *)((char *)workspace + off_delta);
+    AttnBwdMaps m;
+    if (!get_bwd_maps(qkv, d_out, dqkv, acc, B, N, H, m)) return XQ_ERR_UNSUPPORTED;
+    const int nK = (N + AT_BN - 1) / AT_BN;
+    const int Npad = (N + AT_BM - 1) / AT_BM * AT_BM;
+    XQ_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * H * N * AT_D * sizeof(float), st));
+    {
+        const long long threads = (long long)B * H * Npad * 8;
+        attn_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16 *)out, (const __nv_bfloat16 *)d_out,
+                                                                              lse2, lseP, deltaP, B, N, H, Npad);
+        XQ_LAUNCH_CHECK("attn_bwd_prep_kernel");
+    }
+    const size_t smem = AttnBwdSmem::BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long ctas = (long long)B * H * nK;
+    if (ctas > 0x7fffffffLL) return XQ_ERR_ARG;
+    attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, N, H, nK, Npad,
+                                                              scale * 1.4426950408889634f, scale);
+    XQ_LAUNCH_CHECK("attn_bwd_kernel");
+    {
+        const long long threads = (long long)B * H * N * 8;
+        attn_dq_convert_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(acc, (__nv_bfloat16 *)dqkv, B, N, H, scale);
+        XQ_LAUNCH_CHECK("attn_dq_convert_kernel");
+    }
+    return XQ_OK;
+}
+
+}  // extern "C"
+
+namespace xq {
 }  // namespace xq
 
 extern "C" {

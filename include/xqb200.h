@@ -242,6 +242,14 @@ int xq_vit_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, 
  *   scale = head_dim^-0.5 (Attention.scale).  Any N >= 1; qkv / out 16-byte aligned. */
 int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H, int head_dim, float scale, void *stream);
 
+/*   Backward of xq_vit_attn_fwd: d_out bf16 [B,N,H*64] -> dqkv bf16 [B,N,3,H,64] (the gradient of the packed projection,
+ *   written in place of autograd's three permuted tensors + stack).  `out` and `lse2` are the forward's results.
+ *   workspace (1024-byte aligned, xq_vit_attn_bwd_workspace_bytes): fp32 dQ accumulator [B*H,N,64] (TMA reduce-add across
+ *   the key blocks) + the padded statistics.  3 launches + 1 memset. */
+size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H);
+int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, int B, int N, int H,
+                    int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream);
+
 /*
  * ---- loss stack -------------------------------------------------------------------
  * LPIPS stage distance (tokenizer/tokenizer_image/lpips.py:79-90): for one VGG stage with feature maps f0, f1
