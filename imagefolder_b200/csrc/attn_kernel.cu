@@ -721,7 +721,7 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     using namespace xq;
     if (!qkv || !out || !d_out || !lse2 || !dqkv || !workspace || B <= 0 || N <= 0 || H <= 0) return XQ_ERR_ARG;
     if (head_dim != AT_D) return XQ_ERR_UNSUPPORTED;
-    if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)d_out & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)workspace & 1023))
+    if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)d_out & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)workspace & 255))
         return XQ_ERR_ARG;
     size_t off_lse, off_delta;
     if (workspace_bytes < attn_bwd_ws_layout(B, N, H, &off_lse, &off_delta)) return XQ_ERR_WORKSPACE;

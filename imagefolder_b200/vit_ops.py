@@ -3,8 +3,10 @@
 `run_blocks(vit, x)` walks `vit.blocks` + `vit.norm` exactly like the reference
 (dino_enc/dinov2.py:183-190 -> vision_transformer.py:336-339) but replaces every chain
    [+ residual] -> LayerScale -> DropPath -> add -> LayerNorm -> cast-to-bf16
-by ONE kernel (`xq_vit_residual_ln_fwd`) and GELU by one bf16 kernel; GEMMs stay on cuBLAS and
-attention on the SDPA library kernel.  The residual stream is fp32 and the GEMM operands bf16,
+by ONE kernel (`xq_vit_residual_ln_fwd`), GELU by one bf16 kernel and attention by the tcgen05 / TMEM / TMA flash
+kernels of csrc/attn_kernel.cu (`xq_vit_attn_fwd/bwd`, reading the packed qkv projection in place and writing d(qkv)
+in the packed layout); the projection GEMMs stay on cuBLAS.  Attention dropout > 0 (no shipped config) and head
+dims other than 64 use the SDPA library kernel.  The residual stream is fp32 and the GEMM operands bf16,
 which is what bf16 autocast gives the reference, so the numerics are the reference's.
 """
 from __future__ import annotations
@@ -118,6 +120,49 @@ def gelu_bias(x, bias=None):
     return _GeluBias.apply(x, bias)
 
 
+ATTN_TC_ENABLED = [True]      # the tcgen05 attention kernels (csrc/attn_kernel.cu); tools flip it to time the library path
+
+
+def attn_tc_ok(qkv, num_heads: int, dropout_p: float) -> bool:
+    """xq_vit_attn_fwd/bwd cover what the shipped configs run: bf16, head_dim 64, no mask, attn_drop = 0."""
+    return (ATTN_TC_ENABLED[0] and qkv.is_cuda and qkv.dtype == torch.bfloat16 and dropout_p == 0.0
+            and qkv.shape[-1] == 3 * num_heads * 64)
+
+
+def attn_tc_forward(qkv, num_heads: int):
+    """qkv bf16 [B,N,3*H*64] (packed projection, read in place) -> (out bf16 [B,N,H*64], lse2 fp32 [B,H,N])."""
+    B, N, C3 = qkv.shape
+    qkv = qkv.contiguous()
+    out = torch.empty(B, N, C3 // 3, dtype=torch.bfloat16, device=qkv.device)
+    lse2 = torch.empty(B, num_heads, N, dtype=torch.float32, device=qkv.device)
+    L = _lib()
+    _call("xq_vit_attn_fwd", 1, L.xq_vit_attn_fwd, _ptr(qkv), _ptr(out), _ptr(lse2), B, N, num_heads, 64, 0.125,
+          _stream(qkv.device), nbytes=qkv.numel() * 2 + out.numel() * 2 + lse2.numel() * 4)
+    return out, lse2
+
+
+_ATTN_WS = {}
+
+
+def attn_tc_backward(qkv, out, lse2, g, num_heads: int):
+    """d(out) bf16 [B,N,H*64] -> d(qkv) bf16 [B,N,3*H*64] written directly in the packed layout."""
+    B, N, C3 = qkv.shape
+    g = g.contiguous()
+    if g.dtype != torch.bfloat16:
+        g = g.to(torch.bfloat16)
+    dqkv = torch.empty_like(qkv)
+    L = _lib()
+    nbytes = int(L.xq_vit_attn_bwd_workspace_bytes(B, N, num_heads))
+    key = (qkv.device.index, torch.cuda.current_stream(qkv.device).cuda_stream)
+    ws = _ATTN_WS.get(key)                      # one workspace per (device, stream): calls on a stream are ordered
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+        _ATTN_WS[key] = ws
+    _call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, _ptr(qkv), _ptr(out), _ptr(g), _ptr(lse2), _ptr(dqkv), B, N, num_heads, 64,
+          0.125, _ptr(ws), ws.numel(), _stream(qkv.device), nbytes=qkv.numel() * 4 + out.numel() * 4 + lse2.numel() * 4)
+    return dqkv
+
+
 def _sdpa_packed(qkv, num_heads, dropout_p):
     """q/k/v as strided views of the packed projection (no copies); returns the leaves and the library output."""
     B, N, C3 = qkv.shape
@@ -167,12 +212,22 @@ class _PackedAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, num_heads: int, dropout_p: float):
         B, N, C3 = qkv.shape
-        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
         ctx.dims = (B, N, C3 // 3)
+        ctx.tc = attn_tc_ok(qkv, num_heads, dropout_p)
+        if ctx.tc:
+            qkv = qkv.contiguous()
+            out, lse2 = attn_tc_forward(qkv, num_heads)
+            ctx.save_for_backward(qkv, out, lse2)
+            ctx.heads = num_heads
+            return out
+        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
         return ctx.inner[3].detach().transpose(1, 2).reshape(B, N, C3 // 3)
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.tc:
+            qkv, out, lse2 = ctx.saved_tensors
+            return attn_tc_backward(qkv, out, lse2, g, ctx.heads), None, None
         inner, ctx.inner = ctx.inner, None
         dqkv, _ = _sdpa_packed_backward(inner, ctx.dims, g, False)
         return dqkv, None, None
@@ -192,17 +247,28 @@ class _QKVAttention(torch.autograd.Function):
         B, N, C = y.shape
         Wb = W.to(torch.bfloat16)
         qkv = torch.addmm(b.to(torch.bfloat16), y.reshape(B * N, C), Wb.t()).view(B, N, 3 * C)
-        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
         ctx.dims = (B, N, C)
+        ctx.tc = attn_tc_ok(qkv, num_heads, dropout_p)
+        if ctx.tc:
+            out, lse2 = attn_tc_forward(qkv, num_heads)
+            ctx.save_for_backward(y, Wb, qkv, out, lse2)
+            ctx.heads = num_heads
+            return out
+        ctx.inner = _sdpa_packed(qkv, num_heads, dropout_p)
         ctx.save_for_backward(y, Wb)
         return ctx.inner[3].detach().transpose(1, 2).reshape(B, N, C)
 
     @staticmethod
     def backward(ctx, g):
-        inner, ctx.inner = ctx.inner, None
-        y, Wb = ctx.saved_tensors
         B, N, C = ctx.dims
-        dqkv, db = _sdpa_packed_backward(inner, ctx.dims, g, ctx.needs_input_grad[2])
+        if ctx.tc:
+            y, Wb, qkv, out, lse2 = ctx.saved_tensors
+            dqkv = attn_tc_backward(qkv, out, lse2, g, ctx.heads)
+            db = dqkv.view(B * N, 3 * C).sum(0, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        else:
+            inner, ctx.inner = ctx.inner, None
+            y, Wb = ctx.saved_tensors
+            dqkv, db = _sdpa_packed_backward(inner, ctx.dims, g, ctx.needs_input_grad[2])
         d2 = dqkv.view(B * N, 3 * C)
         dy = (d2 @ Wb).view(B, N, C) if ctx.needs_input_grad[0] else None
         dW = (d2.t() @ y.reshape(B * N, C)).float() if ctx.needs_input_grad[1] else None

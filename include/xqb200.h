@@ -244,7 +244,7 @@ int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H
 
 /*   Backward of xq_vit_attn_fwd: d_out bf16 [B,N,H*64] -> dqkv bf16 [B,N,3,H,64] (the gradient of the packed projection,
  *   written in place of autograd's three permuted tensors + stack).  `out` and `lse2` are the forward's results.
- *   workspace (1024-byte aligned, xq_vit_attn_bwd_workspace_bytes): fp32 dQ accumulator [B*H,N,64] (TMA reduce-add across
+ *   workspace (256-byte aligned, xq_vit_attn_bwd_workspace_bytes): fp32 dQ accumulator [B*H,N,64] (TMA reduce-add across
  *   the key blocks) + the padded statistics.  3 launches + 1 memset. */
 size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H);
 int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, int B, int N, int H,

@@ -125,3 +125,20 @@ def test_argument_validation_of_the_newer_entry_points_without_gpu():
     assert L.xq_vit_patchify(f, one, 2, 3, 60, 64, 16, None) == -4                     # H % patch != 0
     assert L.xq_vit_residual_ln_bwd(None, None, None, None, None, None, None, None, None, None, 1, 8, 768, None, None, None,
                                     None, None, None, None, 0, None) == -1
+
+
+def test_attention_entry_points_validate_arguments_without_gpu():
+    """xq_vit_attn_fwd / bwd (csrc/attn_kernel.cu): NULL pointers, unsupported head dims, misaligned buffers and short
+    workspaces are refused with error codes before anything is launched."""
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    assert L.xq_vit_attn_fwd(None, None, None, 1, 16, 1, 64, 0.125, None) == -1
+    assert L.xq_vit_attn_fwd(4096, 8192, 12288, 1, 16, 1, 32, 0.125, None) == -4      # head_dim != 64: unsupported
+    assert L.xq_vit_attn_fwd(4097, 8192, 12288, 1, 16, 1, 64, 0.125, None) == -1      # qkv not 16-byte aligned
+    assert L.xq_vit_attn_fwd(4096, 8192, 12288, 0, 16, 1, 64, 0.125, None) == -1
+    assert L.xq_vit_attn_bwd_workspace_bytes(0, 16, 1) == 0
+    need = L.xq_vit_attn_bwd_workspace_bytes(2, 513, 12)
+    assert need >= 2 * 12 * 513 * 64 * 4 + 2 * 2 * 12 * 640 * 4
+    assert L.xq_vit_attn_bwd(None, None, None, None, None, 1, 16, 1, 64, 0.125, None, 0, None) == -1
+    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, 2, 513, 12, 64, 0.125, 4096, need - 1, None) == -2   # workspace
+    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, 2, 513, 12, 128, 0.125, 4096, need, None) == -4

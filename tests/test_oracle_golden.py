@@ -168,3 +168,82 @@ def test_oracle_edge_cases_ties_and_degenerate_sizes():
     np.testing.assert_array_equal(xo.rows_to_nchw(xo.area_pool_rows(f, 5), f.shape), f)
     np.testing.assert_allclose(xo.area_pool_rows(f, 1).reshape(2, 3), f.reshape(2, 3, -1).mean(-1), rtol=1e-6, atol=1e-6)
     np.testing.assert_array_equal(xo.bicubic_up(xo.nchw_to_rows(f), 2, 3, 5, 5, 5), f)
+
+
+# ---- round 2: BASELINE-shaped codebooks (configs #2 / #3) and an unscreened multi-scale case ------------------------
+def _det_inputs(shape, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).numpy()
+
+
+def _det_param(name, shape):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from vit_det_init import det_tensor
+    return det_tensor(name, shape).numpy()
+
+
+def big_vq_inputs(g):
+    V, C, B, hw, seed = (int(g[k]) for k in ("V", "C", "B", "hw", "seed"))
+    E = _det_param("embedding.weight", (V, C))
+    z = _det_inputs((B, C, hw, hw), seed)
+    g_out = _det_inputs((B, C, hw, hw), seed + 1)
+    return E, z, g_out
+
+
+@pytest.mark.parametrize("name", ["vq8192_c32", "vq16384_c32"])
+def test_vq_baseline_shaped_codebooks(name):
+    """reference goldens at V = 8192 / 16384, C = 32 (BASELINE configs #2 / #3), 1024 rows."""
+    g = load_golden(name)
+    E, z, g_out = big_vq_inputs(g)
+    fwd = xo.vq_forward(z, E, beta=0.25, codebook_norm=True)
+    assert check_idx(fwd["idx"], g["idx"], fwd["margin"]) == 0
+    close(fwd["out"][:, :, ::2, ::2], g["out_sub"])
+    close(fwd["vq"], g["vq"])
+    close(fwd["commit"], g["commit"])
+    gz, gE = xo.vq_backward(fwd, E, g_out, float(g["w_vq"]), float(g["w_commit"]), 0.25, True)
+    close(gz[:, :, ::2, ::2], g["gz_sub"])
+    gE_ref = np.zeros_like(gE)
+    gE_ref[g["gE_rows"]] = g["gE_vals"]
+    close(gE, gE_ref)
+
+
+def msvr_unscreened_inputs(g):
+    V, C, B, seed = (int(g[k]) for k in ("V", "C", "B", "seed"))
+    pn = [int(p) for p in g["patch_nums"]]
+    E = _det_param("embedding.weight", (V, C))
+    phi_w = np.stack([_det_param(f"quant_resi.qresi_ls.{k}.weight", (C, C, 3, 3)) for k in range(4)])
+    phi_b = np.stack([_det_param(f"quant_resi.qresi_ls.{k}.bias", (C,)) for k in range(4)])
+    f = _det_inputs((B, C, pn[-1], pn[-1]), seed)
+    return E, phi_w, phi_b, f, pn
+
+
+def count_first_divergences(idx_mine, idx_ref, margins, B, tie=1e-5):
+    """Per sample: the first scale where the index lists differ must differ only at near-tie positions (a flipped index
+    changes the residual of every later scale, so later scales of that sample are not comparable).  Returns the number of
+    samples that diverged and the number of differing tokens at their first divergent scale."""
+    diverged, tokens = 0, 0
+    for b in range(B):
+        for si in range(len(idx_ref)):
+            bad = np.asarray(idx_mine[si][b]) != np.asarray(idx_ref[si][b])
+            if bad.any():
+                m = np.asarray(margins[si]).reshape(B, -1)[b]
+                assert np.all(m[bad] < tie), f"sample {b} scale {si}: index mismatch with top-2 margin {m[bad].max():.3e}"
+                diverged += 1
+                tokens += int(bad.sum())
+                break
+    return diverged, tokens
+
+
+def test_msvr_unscreened_seed_mismatches_are_near_ties():
+    """make_golden.case_vq2 screens seeds for near-ties; this case does not: mismatches against the reference's indices
+    are COUNTED and each must be a provable near-tie."""
+    g = load_golden("msvr_unscreened")
+    E, phi_w, phi_b, f, pn = msvr_unscreened_inputs(g)
+    fw = xo.vq2_forward(f, E, phi_w, phi_b, pn, using_znorm=True)
+    ref = [g[f"idx{si}"] for si in range(len(pn))]
+    diverged, tokens = count_first_divergences(fw["idx"], ref, fw["margins"], f.shape[0])
+    print("msvr_unscreened: samples diverged", diverged, "tokens at first divergence", tokens)
+    assert diverged <= 1          # observed 0 on this seed; a single near-tie flip would still be legitimate
