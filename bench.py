@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--workload", type=str, default=WORKLOAD)
     p.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extra", action="store_true", help="skip the MSVR10P2-4096 ours-vs-eager extra measurement")
     p.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline step (0 = auto)")
     return p.parse_args()
 
@@ -134,35 +135,49 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch.distributed as dist
+class Ctx:
+    """process-wide state shared by every measurement of this run (one process per GPU)."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        torch.backends.cuda.matmul.allow_tf32 = True   # xqgan_train.py:5-6
+        torch.backends.cudnn.allow_tf32 = True
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(list(vals), device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def make_step(ctx, workload, B, impl):
+    """model + optimizer + the training-step closure of one workload (the body of xqgan_train.py:448-462 restricted to
+    the in-scope path).  impl 'eager' = the reference's way of computing the path in plain PyTorch on the same GPU."""
     import torch.nn.functional as F
-    from imagefolder_b200 import _capi, config as xcfg
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cuda.matmul.allow_tf32 = True   # xqgan_train.py:5-6
-    torch.backends.cudnn.allow_tf32 = True
-
-    model, margs = build_model(a.workload, dev)
+    from imagefolder_b200 import config as xcfg
+    model, margs = build_model(workload, ctx.dev)
     model.train()
     fwd_module = model
-    if a.impl == "eager":
+    if impl == "eager":
         from oracle.eager_ref import EagerTokenizer   # baseline leg only: reference-style eager ops, no libxqb200
         fwd_module = EagerTokenizer(model)
-    net = torch.nn.parallel.DistributedDataParallel(fwd_module, device_ids=[local]) if world > 1 else fwd_module
+    net = (torch.nn.parallel.DistributedDataParallel(fwd_module, device_ids=[ctx.local]) if ctx.world > 1 else fwd_module)
     opt = torch.optim.AdamW(model.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
-    B = a.batch
-    g = torch.Generator(device=dev).manual_seed(1234 * world + rank)
-    imgs_dev = torch.rand(B, 3, 256, 256, device=dev, generator=g) * 2 - 1
-    imgs_host = imgs_dev.cpu().pin_memory()
     alpha, beta, delta = xcfg.perturbation_schedule(margs, 0)
 
     def step(x):
@@ -174,10 +189,141 @@ def run_ours(a):
         opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    g = torch.Generator(device=ctx.dev).manual_seed(1234 * ctx.world + ctx.rank)
+    imgs_dev = torch.rand(B, 3, 256, 256, device=ctx.dev, generator=g) * 2 - 1
+    return model, margs, step, imgs_dev
+
+
+def time_resident(ctx, step, imgs_dev, steps, warmup, collect_kernels=False):
+    """W warm-up steps, then exactly K steps bracketed by barrier + synchronize, CUDA events on the launching stream."""
+    from imagefolder_b200 import _capi
+    for _ in range(warmup):
+        step(imgs_dev)
+    ctx.barrier()
+    if collect_kernels:
+        _capi.TIMING = {}
+    _capi.LAUNCHES[0] = 0
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(imgs_dev)
+    e1.record()
+    ctx.barrier()
+    ms = e0.elapsed_time(e1)
+    timing, _capi.TIMING = _capi.TIMING, None
+    return ms, _capi.LAUNCHES[0], (timing or {})
+
+
+def kernel_table(timing, steps):
+    rows = []
+    for name, evs in timing.items():
+        tot = sum(t[0].elapsed_time(t[1]) for t in evs)
+        nb = sum(t[2] for t in evs)
+        rows.append({"entry": name, "calls_per_step": len(evs) / steps, "ms_per_step": tot / steps,
+                     "ms_per_call": tot / len(evs), "alg_GBps": (nb / (tot * 1e-3) / 1e9) if nb else None})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows
+
+
+def ncu_traffic_table():
+    """dram bytes per launch keyed by kernel name, read from the committed ncu summaries (profiles/ncu_traffic.json,
+    written by tools/ncu_summarize.py from the .ncu-rep captures); None when a kernel / shape has no capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def quantizer_roofline(workload, margs, B, kern_ms, entry, hbm, tf, src):
+    """Roofline object of the quantizer kernel the metric names, per workload:
+       VQ / VP2  -> tensor roof of the contraction 2*rows*V*C   (vq_search_tc_kernel)
+       MSVR      -> same contraction summed over the 10 scales, plus the 10-step dependent-chain note (ms_forward_kernel)
+       MSBR      -> HBM roof of the streaming BSQ kernels (no contraction: a sign test)."""
+    if not kern_ms:
+        return None
+    C, V = margs.codebook_embed_dim, margs.codebook_size
+    pq = margs.product_quant
+    multi = len(margs.v_patch_nums) > 1
+    rows_branch = B * (sum(p * p for p in margs.v_patch_nums) if multi else margs.num_latent_tokens // pq)
+    hw = margs.v_patch_nums[-1] ** 2 if multi else margs.num_latent_tokens // pq
+    traffic = ncu_traffic_table()
+    if getattr(margs, "lfq", False):
+        # per branch: read f, write f_hat (fp32 [B,C,H,W]) + int64 indices + Phi weights
+        bytes_alg = 2 * B * C * hw * 4 + rows_branch * 8 + 4 * (C * C * 9 + C) * 4
+        gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "ms_forward_kernel (BSQ mode) + bsq_entropy kernels; timed = one xq_ms_forward call (one PQ branch)",
+                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                "traffic": traffic.get(f"ms_forward_kernel/{workload}/B{B}"), "peak_source": src, "kernel_ms": kern_ms,
+                "algorithmic_bytes": bytes_alg,
+                "note": "implicit codebook (sign test): no contraction, pure streaming; the kernel is a 10-step dependent chain "
+                        "per image, so latency x 10 bounds it before HBM does"}
+    bytes_alg = rows_branch * C * 4 + V * C * 4 + rows_branch * 8 + rows_branch * C * 4
+    if multi:
+        bytes_alg = 2 * B * C * hw * 4 + rows_branch * 8 + V * C * 4 + 4 * (C * C * 9 + C) * 4
+    flops_alg = 2.0 * rows_branch * V * C
+    gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
+    tfs = flops_alg / (kern_ms * 1e-3) / 1e12
+    if multi:
+        name = "ms_forward_kernel (fused 10-scale residual loop in shared memory, FP32 search); timed = one xq_ms_forward call (one PQ branch)"
+        note = ("10 DEPENDENT scales per image: latency x 10 bounds the kernel; the per-scale searches are CUDA-core FP32 "
+                "(DESIGN.md section 9), so the tensor fraction is reported against the contraction's roof, not achieved on tensor cores")
+        tkey = f"ms_forward_kernel/{workload}/B{B}"
+    else:
+        tc = (C in (32, 64)) and os.environ.get("XQ_VQ_ALGO", "auto")[0] != "e"
+        name = ("vq_search_tc_kernel (tcgen05 TF32 screening + exact fp32 rescoring)" if tc else
+                "vq_search_kernel (exact fp32 CUDA-core)") + "; timed = the xq_vq_forward call (codebook prep + search + loss finalize)"
+        note = "contraction-bound, not HBM-bound (arithmetic intensity ~1900 FLOP/B, DESIGN.md section 5)"
+        tkey = f"vq_search_tc_kernel/N{rows_branch}/V{V}/C{C}"
+    out = {"bound": "tensor", "kernel": name, "achieved": tfs, "peak": tf, "unit": "TFLOP/s", "frac": tfs / tf,
+           "traffic": traffic.get(tkey), "peak_source": src + " (dense bf16 cuBLAS; no TF32 peak is measured on this pool)",
+           "kernel_ms": kern_ms, "algorithmic_flops": flops_alg, "algorithmic_bytes": bytes_alg, "hbm_gbs": gbs,
+           "hbm_frac": gbs / hbm, "note": note + "; traffic = dram bytes/launch from the committed ncu capture of this "
+           "kernel + shape (profiles/ncu_traffic.json), null when that shape was not captured"}
+    if not multi:
+        # TMEM -> register read floor of the tcgen05 path: every approximate score (N*V fp32) crosses the tcgen05.ld port once
+        out["tmem_read_floor_ms"] = rows_branch * V * 4 / (125.0 * 148 * 1.9e9) * 1e3
+    return out
+
+
+def extra_msvr(ctx, a):
+    """The north star's second target, made driver-visible: MSVR10P2-4096 at per-GPU batch 128, this framework vs the
+    reference's own way of computing the path in PyTorch eager, on the SAME ranks, back to back."""
+    import gc
+    res = {}
+    for impl, steps, warm in (("ours", 3, 2), ("eager", 2, 1)):
+        model, margs, step, imgs = make_step(ctx, "MSVR10P2-4096", 128, impl)
+        ms, launches, timing = time_resident(ctx, step, imgs, steps, warm, collect_kernels=(impl == "ours"))
+        (ms,) = ctx.max_over_ranks(ms)
+        res[impl] = {"img_s": ctx.world * 128 * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "warmup": warm}
+        if impl == "ours":
+            res["ours"]["gpu_launches"] = launches
+            if "xq_ms_forward" in timing:
+                ts = [t[0].elapsed_time(t[1]) for t in timing["xq_ms_forward"]]
+                hbm, tf, src = peaks()
+                res["roofline"] = quantizer_roofline("MSVR10P2-4096", margs, 128, sum(ts) / len(ts), "xq_ms_forward", hbm, tf, src)
+        del model, step, imgs, timing
+        gc.collect()
+        torch.cuda.empty_cache()
+    return {"workload": "MSVR10P2-4096 tokenizer training step, per-GPU batch 128, 256x256, ViT-B enc/dec (same step "
+                        "definition as the headline)",
+            "msvr_img_s": res["ours"]["img_s"], "msvr_eager_img_s": res["eager"]["img_s"],
+            "msvr_speedup": res["ours"]["img_s"] / res["eager"]["img_s"], "ours": res["ours"], "eager": res["eager"],
+            "roofline": res.get("roofline"),
+            "note": "eager = oracle/eager_ref.EagerTokenizer: the reference's op sequence (materialised N x V distances, per-scale "
+                    "Python loop, .item() usage syncs, SDPA + unfused ViT glue) in PyTorch eager with bf16 autocast"}
+
+
+def run_ours(a):
+    import gc
+    from imagefolder_b200 import _capi, vit_ops
+    ctx = Ctx()
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    model, margs, step, imgs_dev = make_step(ctx, a.workload, a.batch, a.impl)
+    B = a.batch
+    imgs_host = imgs_dev.cpu().pin_memory()
+    barrier = ctx.barrier
 
     for _ in range(a.warmup):
         step(imgs_dev)
@@ -185,7 +331,6 @@ def run_ours(a):
     torch.cuda.reset_peak_memory_stats()
     # a generation-2 Python GC pass over the module / autograd heap takes hundreds of ms and, when it lands inside a
     # timed region, drains the launch queue: collect now and keep the collector off until both regions are done
-    import gc
     gc.collect()
     gc.disable()
 
@@ -193,37 +338,19 @@ def run_ours(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    _capi.TIMING = {}
-    _capi.LAUNCHES[0] = 0
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        step(imgs_dev)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _capi.LAUNCHES[0]
-    timing = _capi.TIMING
-    _capi.TIMING = None
-    kern_ms = None
-    if "xq_vq_forward" in timing:
-        ts = [t[0].elapsed_time(t[1]) for t in timing["xq_vq_forward"]]
-        kern_ms = sum(ts) / len(ts)
-    elif "xq_ms_forward" in timing:
-        ts = [t[0].elapsed_time(t[1]) for t in timing["xq_ms_forward"]]
-        kern_ms = sum(ts) / len(ts)
-
-    # per-entry-point table of OUR kernels inside the timed steps (CUDA events on the launching stream)
-    kern_table = []
-    for name, evs in timing.items():
-        tot = sum(t[0].elapsed_time(t[1]) for t in evs)
-        nb = sum(t[2] for t in evs)
-        kern_table.append({"entry": name, "calls_per_step": len(evs) / a.steps, "ms_per_step": tot / a.steps,
-                           "ms_per_call": tot / len(evs),
-                           "alg_GBps": (nb / (tot * 1e-3) / 1e9) if nb else None})
-    kern_table.sort(key=lambda r: -r["ms_per_step"])
+    ms, launches, timing = time_resident(ctx, step, imgs_dev, a.steps, 0, collect_kernels=True)
+    kern_ms, kern_entry = None, None
+    for entry in ("xq_vq_forward", "xq_ms_forward"):
+        if entry in timing:
+            ts = [t[0].elapsed_time(t[1]) for t in timing[entry]]
+            kern_ms, kern_entry = sum(ts) / len(ts), entry
+            break
+    kern_table = kernel_table(timing, a.steps)
     timing.clear()          # release the CUDA events before the next region
+    if a.impl == "ours" and vit_ops.ATTN_TC_ENABLED[0]:
+        # the fused path must be the one that ran (a silent library fallback would hide behind the step time)
+        names = {r["entry"] for r in kern_table}
+        assert {"xq_vit_attn_fwd", "xq_vit_attn_bwd", "xq_vit_residual_ln_fwd", "xq_vit_gelu_fwd"} <= names, names
 
     # ---- timed region 2: end to end through the public API with HOST buffers
     # one-off setup outside the clock (a data loader allocates its pinned buffers and copy stream once; cudaHostAlloc
@@ -262,40 +389,27 @@ def run_ours(a):
     gc.enable()
     clk = clocks.stop() if rank == 0 else None
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = ctx.max_over_ranks(ms, ms_e2e)
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
+    extra = None
+    if a.impl == "ours" and not a.no_extra:
+        # free the headline model before the second workload (all ranks take part: DDP collectives inside)
+        state_for_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()} if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
+        cfg_for_cpu = model.config
+        del step, imgs_dev
+        model = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        extra = _safe(lambda: extra_msvr(ctx, a))
+    else:
+        state_for_cpu, cfg_for_cpu = (model.state_dict(), model.config)
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return
     hbm, tf, src = peaks()
-    q = model.quantizes[0] if model.product_quant > 1 else model.quantize
-    C, V = margs.codebook_embed_dim, margs.codebook_size
-    rows = B * (margs.num_latent_tokens if len(margs.v_patch_nums) == 1 else sum(p * p for p in margs.v_patch_nums))
-    bytes_alg = rows * C * 4 + V * C * 4 + rows * 8 + rows * C * 4     # z + codebook + int64 idx + z_q
-    flops_alg = 2.0 * rows * V * C
-    roof = None
-    if kern_ms:
-        gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
-        tfs = flops_alg / (kern_ms * 1e-3) / 1e12
-        tc = (C in (32, 64)) and os.environ.get("XQ_VQ_ALGO", "auto")[0] != "e"
-        # TMEM -> register read floor of the tcgen05 path: every approximate score (N*V fp32) crosses the tcgen05.ld
-        # port once.  Measured in-kernel (tools/vq_tc_trace.py): 2 co-resident CTAs each drain a 64 KB tile per ~1.05 k clk
-        # = ~125 B/clk per SM, unchanged with 4 or 8 epilogue warps per CTA (B300_MICROARCH.md quotes 64 B/cyc per reader)
-        tmem_floor_ms = rows * V * 4 / (125.0 * 148 * 1.9e9) * 1e3
-        roof = {"bound": "tensor", "kernel": ("vq_search_tc_kernel (tcgen05 TF32 screening + exact fp32 rescoring)" if tc
-                                               else "vq_search_kernel (exact fp32 CUDA-core)") +
-                          "; timed = the xq_vq_forward call (codebook prep + search + loss finalize)",
-                "achieved": tfs, "peak": tf, "unit": "TFLOP/s", "frac": tfs / tf, "traffic": 10.6e6,
-                "peak_source": src + " (dense bf16 cuBLAS; no TF32 peak is measured on this pool)",
-                "kernel_ms": kern_ms, "algorithmic_flops": flops_alg, "algorithmic_bytes": bytes_alg,
-                "hbm_gbs": gbs, "hbm_frac": gbs / hbm, "tmem_read_floor_ms": tmem_floor_ms,
-                "note": "contraction-bound, not HBM-bound (arithmetic intensity ~1900 FLOP/B, DESIGN.md section 5); "
-                        "traffic = dram bytes/launch from the round-1 ncu capture (profiles/)"}
+    roof = quantizer_roofline(a.workload, margs, B, kern_ms, kern_entry, hbm, tf, src)
     if a.impl == "eager":
         roof = None
     out = {
@@ -315,14 +429,16 @@ def run_ours(a):
         "our_kernels_ms_per_step": sum(r["ms_per_step"] for r in kern_table),
         "roofline_top_kernel": _safe(lambda: top_kernel_roofline(
             kern_table, hbm, ms / a.steps,
-            {"xq_vit_residual_ln_bwd": 1.788e9} if (a.workload == "VQ-8192" and B == 256) else None)),
-        "last_loss": loss_host,
+            {k.split("/")[0]: v for k, v in ncu_traffic_table().items() if k.endswith(f"/{a.workload}/B{B}")})),
+        "last_loss": loss_host, "extra": extra,
+        "parity_note": "token indices are bit-exact against the reference's CPU fp32 path except on provable near-ties "
+                       "(top-2 margin < 1e-5; counted in tests/test_gpu_quantizers.py::test_msvr_unscreened_seed_counts_mismatches_on_gpu)",
     }
     if not a.no_cpu_baseline and world == 1 and a.impl == "ours":
-        out["cpu_baseline"] = cpu_arm(a, steps=1, warmup=0, state=model.state_dict(), margs=model.config)
+        out["cpu_baseline"] = cpu_arm(a, steps=1, warmup=0, state=state_for_cpu, margs=cfg_for_cpu)
     print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------

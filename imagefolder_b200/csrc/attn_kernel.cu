@@ -7,10 +7,10 @@
 // head-merged output [B,N,H*64], so that no permute / contiguous copy exists on either side.
 //
 // Forward, one CTA per (batch, head, 128-query tile), 2 CTAs per SM (256 TMEM columns each):
-//   warp 0   TMA producer : Q tile once, K / V row tiles (128 keys x 64) through 2-stage rings
-//   warp 1   MMA issuer   : S = Q K^T   (kind::f16, A,B K-major smem, N = 128 or the 16-rounded tail)  -> TMEM[0,128)
+//   warp 4   TMA producer : Q tile once per tile, K / V row tiles (128 keys x 64) through 2-stage rings
+//   warp 5   MMA issuer   : S = Q K^T   (kind::f16, A,B K-major smem, N = 128 or the 16-rounded tail)  -> TMEM[0,128)
 //                           O += P V    (A = P from TMEM[128,192), B = V MN-major smem, N = 64)        -> TMEM[192,256)
-//   warps 4-7 softmax     : one query row per thread (TMEM lane): S -> registers, running max with LAZY rescaling of O
+//   warps 0-3 softmax     : one query row per thread (TMEM lane): S -> registers, running max with LAZY rescaling of O
 //                           (only when the row max grows by more than 2^8), P = exp2(S*c - m*c) -> bf16 -> TMEM,
 //                           epilogue O / l -> bf16 -> swizzled smem -> TMA store (rows beyond N are clipped by the map)
 //   sequence lengths need not be multiples of anything: the last key block is issued with N = ceil16(valid keys) and
@@ -37,7 +37,8 @@ struct AttnFwdSmem {
     static constexpr int Q = 0;
     static constexpr int K = AT_TILE;
     static constexpr int V = AT_TILE * (1 + AT_NS);
-    static constexpr int BAR = AT_TILE * (1 + 2 * AT_NS);
+    static constexpr int O = AT_TILE * (1 + 2 * AT_NS);     // output staging (the Q tile is re-loaded early for the next tile)
+    static constexpr int BAR = AT_TILE * (2 + 2 * AT_NS);
     static constexpr int BYTES = BAR + 256;
 };
 
@@ -48,99 +49,126 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// Development-only clock trace (compiled in with -DXQ_ATTN_TRACE for tools/attn_trace.py; absent from libxqb200.so)
+#ifdef XQ_ATTN_TRACE
+__device__ long long *g_attn_trace = nullptr;
+#define XQ_TR(cond, slot) do { if ((cond) && g_attn_trace && blockIdx.x == 0) g_attn_trace[(slot)] = clock64(); } while (0)
+#else
+#define XQ_TR(cond, slot) do { } while (0)
+#endif
+
+// PERSISTENT: gridDim.x CTAs (2 per SM) walk the (batch*head, query tile) list with stride gridDim.x; all pipeline state
+// (ring stages, barrier phases) runs on across tiles, so the producer prefetches the next tile's Q / K / V while the softmax
+// warps are still in the epilogue of the current one and the prologue cost (TMEM allocation, descriptor fetch, first-load
+// latency) is paid once per CTA instead of once per tile.
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, float *__restrict__ lse2,
-                int N, int H, int nQ, float c /* softmax scale * log2(e) */) {
+                int N, int H, int nQ /* query tiles per (b,h) handled here */, int n_tiles, float c /* softmax scale * log2(e) */) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnFwdSmem::BAR);
     uint64_t *q_full = bars + 0;
-    uint64_t *k_full = bars + 1;              // [AT_NS]
-    uint64_t *k_empty = bars + 1 + AT_NS;     // [AT_NS]
-    uint64_t *v_full = bars + 1 + 2 * AT_NS;
-    uint64_t *v_empty = bars + 1 + 3 * AT_NS;
-    uint64_t *s_full = bars + 1 + 4 * AT_NS;
+    uint64_t *q_empty = bars + 1;
+    uint64_t *k_full = bars + 2;              // [AT_NS]
+    uint64_t *k_empty = bars + 2 + AT_NS;     // [AT_NS]
+    uint64_t *v_full = bars + 2 + 2 * AT_NS;
+    uint64_t *v_empty = bars + 2 + 3 * AT_NS;
+    uint64_t *s_full = bars + 2 + 4 * AT_NS;
     uint64_t *s_free = s_full + 1;
     uint64_t *p_full = s_full + 2;
     uint64_t *pv_done = s_full + 3;
-    uint32_t *tmem_holder = (uint32_t *)(s_full + 4);
+    uint64_t *o_free = s_full + 4;
+    uint32_t *tmem_holder = (uint32_t *)(s_full + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bh = blockIdx.x / nQ, qt = blockIdx.x - bh * nQ;
-    const int b = bh / H, h = bh - b * H;
-    const int q0 = qt * AT_BM;
     const int nK = (N + AT_BN - 1) / AT_BN;
-    const int colQ = h * AT_D, colK = (H + h) * AT_D, colV = (2 * H + h) * AT_D;
 
     if (tid == 0) {
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int i = 0; i < AT_NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         mbar_init(s_full, 1);
         mbar_init(s_free, 4);
         mbar_init(p_full, 4);
         mbar_init(pv_done, 1);
+        mbar_init(o_free, 4);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_holder);
+    if (warp == 5) tmem_alloc<256>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
     const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
 
-    if (warp < 4) {
+    // warps 0-3 = softmax, warps 4-7 = control (4 = TMA producer, 5 = MMA issuer): the warp scheduler favours the higher
+    // warp id among eligible warps, which keeps the single-thread MMA issuer from being starved by the softmax warps
+    if (warp >= 4) {
         reg_dec<40>();
-        if (warp == 0 && lane == 0) {
+        if (warp == 4 && lane == 0) {
             // ===== TMA producer =====
             tma_prefetch_desc(&tmQKV);
-            mbar_expect_tx(q_full, AT_TILE);
-            tma_load_3d(base + AttnFwdSmem::Q, &tmQKV, colQ, q0, b, q_full);
-            for (int j = 0; j < nK; ++j) {
-                const int st = j % AT_NS;
-                const uint32_t ph = ((j / AT_NS) & 1) ^ 1;
-                mbar_wait(&k_empty[st], ph);
-                mbar_expect_tx(&k_full[st], AT_TILE);
-                tma_load_3d(base + AttnFwdSmem::K + st * AT_TILE, &tmQKV, colK, j * AT_BN, b, &k_full[st]);
-                mbar_wait(&v_empty[st], ph);
-                mbar_expect_tx(&v_full[st], AT_TILE);
-                tma_load_3d(base + AttnFwdSmem::V + st * AT_TILE, &tmQKV, colV, j * AT_BN, b, &v_full[st]);
+            uint32_t it = 0, tl = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+                const int bh = t / nQ, qt = t - bh * nQ;
+                const int b = bh / H, h = bh - b * H;
+                const int colQ = h * AT_D, colK = (H + h) * AT_D, colV = (2 * H + h) * AT_D;
+                mbar_wait(q_empty, (tl & 1) ^ 1);
+                mbar_expect_tx(q_full, AT_TILE);
+                tma_load_3d(base + AttnFwdSmem::Q, &tmQKV, colQ, qt * AT_BM, b, q_full);
+                for (int j = 0; j < nK; ++j, ++it) {
+                    const int st = it % AT_NS;
+                    const uint32_t ph = ((it / AT_NS) & 1) ^ 1;
+                    mbar_wait(&k_empty[st], ph);
+                    mbar_expect_tx(&k_full[st], AT_TILE);
+                    tma_load_3d(base + AttnFwdSmem::K + st * AT_TILE, &tmQKV, colK, j * AT_BN, b, &k_full[st]);
+                    mbar_wait(&v_empty[st], ph);
+                    mbar_expect_tx(&v_full[st], AT_TILE);
+                    tma_load_3d(base + AttnFwdSmem::V + st * AT_TILE, &tmQKV, colV, j * AT_BN, b, &v_full[st]);
+                }
             }
-        } else if (warp == 1 && lane == 0) {
+        } else if (warp == 5 && lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t qa = smem_u32(base + AttnFwdSmem::Q);
-            auto issue_qk = [&](int j) {
-                const int st = j % AT_NS;
-                const int nv = min(AT_BN, N - j * AT_BN);
-                const int nj = (nv + 15) & ~15;
-                mbar_wait(&k_full[st], (j / AT_NS) & 1);
+            const uint64_t qd = desc_k_sw128(smem_u32(base + AttnFwdSmem::Q));
+            uint32_t it = 0, tl = 0;
+            auto issue_qk = [&](uint32_t itx, int j) {
+                const int st = itx % AT_NS;
+                const int nj = (min(AT_BN, N - j * AT_BN) + 15) & ~15;
+                mbar_wait(&k_full[st], (itx / AT_NS) & 1);
                 tc_fence_after();
-                const uint32_t ka = smem_u32(base + AttnFwdSmem::K + st * AT_TILE);
+                const uint64_t kd = desc_k_sw128(smem_u32(base + AttnFwdSmem::K + st * AT_TILE));
                 const uint32_t id = idesc_bf16(AT_BM, nj, 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_k_sw128(qa + k * 32), desc_k_sw128(ka + k * 32), id, k > 0);
+                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(qd, k * 32), desc_adv(kd, k * 32), id, k > 0);
                 umma_commit(&k_empty[st]);
                 umma_commit(s_full);
             };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < nK; ++j) {
-                if (j + 1 < nK) {
-                    mbar_wait(s_free, j & 1);          // softmax holds S_j in registers
-                    tc_fence_after();
-                    issue_qk(j + 1);
-                }
-                const int st = j % AT_NS;
-                const int nv = min(AT_BN, N - j * AT_BN);
-                const int nj = (nv + 15) & ~15;
-                mbar_wait(&v_full[st], (j / AT_NS) & 1);
-                mbar_wait(p_full, j & 1);              // P_j written (and O rescaled)
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+                mbar_wait(q_full, tl & 1);
+                if (it > 0) { mbar_wait(s_free, (it - 1) & 1); }      // the last S of the previous tile is in registers
                 tc_fence_after();
-                const uint32_t va = smem_u32(base + AttnFwdSmem::V + st * AT_TILE);
-                const uint32_t id = idesc_bf16(AT_BM, AT_D, 0, 1);
-                for (int k = 0; k < nj / 16; ++k)
-                    umma_ts(tO, tP + k * 8, desc_mn_sw128(va + k * 2048, 16384, 1024), id, (j | k) != 0);
-                umma_commit(&v_empty[st]);
-                umma_commit(pv_done);
+                issue_qk(it, 0);
+                for (int j = 0; j < nK; ++j, ++it) {
+                    if (j + 1 < nK) {
+                        mbar_wait(s_free, it & 1);          // softmax holds S_j in registers
+                        tc_fence_after();
+                        issue_qk(it + 1, j + 1);
+                        if (j + 2 == nK) umma_commit(q_empty);   // every S MMA of this tile has been issued: Q is dead once they retire
+                    } else if (nK == 1) {
+                        umma_commit(q_empty);
+                    }
+                    const int st = it % AT_NS;
+                    const int nj = (min(AT_BN, N - j * AT_BN) + 15) & ~15;
+                    mbar_wait(&v_full[st], (it / AT_NS) & 1);
+                    mbar_wait(p_full, it & 1);              // P_j written (and O rescaled)
+                    if (j == 0 && tl > 0) mbar_wait(o_free, (tl - 1) & 1);   // the epilogue has read the previous tile's O
+                    tc_fence_after();
+                    const uint64_t vd = desc_mn_sw128(smem_u32(base + AttnFwdSmem::V + st * AT_TILE), 16384, 1024);
+                    const uint32_t id = idesc_bf16(AT_BM, AT_D, 0, 1);
+                    for (int k = 0; k < nj / 16; ++k) umma_ts(tO, tP + k * 8, desc_adv(vd, k * 2048), id, (j | k) != 0);
+                    umma_commit(&v_empty[st]);
+                    umma_commit(pv_done);
+                }
             }
         }
     } else {
@@ -149,114 +177,235 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float m_used = -CUDART_INF_F;     // raw-score max the current P / O are expressed against
-        float l = 0.f;
-        for (int j = 0; j < nK; ++j) {
-            const int nv = min(AT_BN, N - j * AT_BN);       // valid keys in this block
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            uint32_t s[128];
+        uint32_t it = 0, tl = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+            const int bh = t / nQ, qt = t - bh * nQ;
+            const int b = bh / H, h = bh - b * H;
+            const int q0 = qt * AT_BM;
+            float m_used = -CUDART_INF_F;     // raw-score max the current P / O are expressed against
+            float l = 0.f;
+            // a warp whose 32 rows all lie beyond N (last tile of a ragged sequence) only keeps the pipeline's barriers
+            // moving: its P / O rows feed rows the output tensor map clips, so their contents do not matter
+            const bool warp_live = q0 + q * 32 < N;
+            for (int j = 0; j < nK; ++j, ++it) {
+                const int nv = min(AT_BN, N - j * AT_BN);       // valid keys in this block
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                if (!warp_live) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                    if (j > 0) mbar_wait(pv_done, (it - 1) & 1);
+                    if (lane == 0) mbar_arrive(p_full);
+                    continue;
+                }
+                uint32_t s[128];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                if (ch * 32 < nv) tmem_ld32(tS + lane_addr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (ch * 32 < nv) tmem_ld32(tS + lane_addr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[ch * 32]));
+                }
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free);
+                float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+                if (nv == AT_BN) {
+#pragma unroll
+                    for (int i = 0; i < 128; i += 4) {
+                        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[i]));
+                        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[i + 1]));
+                        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[i + 2]));
+                        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[i + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (ch * 32 < nv) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                float x = __uint_as_float(s[ch * 32 + i]);
+                                if (ch * 32 + i >= nv) x = -CUDART_INF_F;
+                                s[ch * 32 + i] = __float_as_uint(x);
+                                mx4[i & 3] = fmaxf(mx4[i & 3], x);
+                            }
+                        }
+                    }
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                if (j > 0) mbar_wait(pv_done, (it - 1) & 1);       // O and the P buffer are quiescent
+                tc_fence_after();
+                const bool grow = (mx - m_used) * c > AT_LAZY;     // j == 0: m_used = -inf -> true
+                if (j == 0) {
+                    m_used = mx;
+                } else if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = grow ? mx : m_used;
+                    const float alpha = ex2_approx((m_used - m_new) * c);
+                    l *= alpha;
+                    m_used = m_new;
+#pragma unroll
+                    for (int c0 = 0; c0 < AT_D; c0 += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(tO + lane_addr + c0, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tO + lane_addr + c0, o);
+                    }
+                }
+                const float mc = m_used * c;
+                float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (ch * 32 < nv) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i]), c, -mc));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i + 1]), c, -mc));
+                            float p2 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i + 2]), c, -mc));
+                            float p3 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i + 3]), c, -mc));
+                            sum0 += p0;
+                            sum1 += p1;
+                            sum2 += p2;
+                            sum3 += p3;
+                            pk[i >> 1] = pack_bf16(p0, p1);
+                            pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+                        }
+                        tmem_st16(tP + lane_addr + ch * 16, pk);
+                    }
+                }
+                l += (sum0 + sum1) + (sum2 + sum3);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
             }
+            // ---- epilogue: O / l -> bf16 -> staging smem -> TMA store (rows beyond N are clipped by the tensor map)
+            mbar_wait(pv_done, (it - 1) & 1);
+            tc_fence_after();
+            uint32_t o[64];
+            tmem_ld32(tO + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+            tmem_ld32(tO + lane_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);
-            float mx = -CUDART_INF_F;
+            if (lane == 0) mbar_arrive(o_free);             // the next tile's first P V may overwrite O
+            const float inv = 1.0f / l;
+            if (q0 + row < N) lse2[(size_t)bh * N + q0 + row] = fmaf(m_used, c, log2f(l));
+            uint8_t *so = base + AttnFwdSmem::O;
+            const uint32_t so_a = smem_u32(so);
+            if (warp == 0 && lane == 0) bulk_wait_read<0>();   // the previous tile's store has finished reading the staging tile
+            named_bar_sync(1, 128);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                if (ch * 32 < nv) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(s[ch * 32 + i]);
-                        if (ch * 32 + i >= nv) x = -CUDART_INF_F;
-                        s[ch * 32 + i] = __float_as_uint(x);
-                        mx = fmaxf(mx, x);
-                    }
-                }
+            for (int u = 0; u < 8; ++u) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(o[8 * u + 0]) * inv, __uint_as_float(o[8 * u + 1]) * inv);
+                v.y = pack_bf16(__uint_as_float(o[8 * u + 2]) * inv, __uint_as_float(o[8 * u + 3]) * inv);
+                v.z = pack_bf16(__uint_as_float(o[8 * u + 4]) * inv, __uint_as_float(o[8 * u + 5]) * inv);
+                v.w = pack_bf16(__uint_as_float(o[8 * u + 6]) * inv, __uint_as_float(o[8 * u + 7]) * inv);
+                sts128(so_a + rowtile_unit(row, u), v);
             }
-            if (j > 0) mbar_wait(pv_done, (j - 1) & 1);       // O and the P buffer are quiescent
-            tc_fence_after();
-            const bool grow = (mx - m_used) * c > AT_LAZY;     // j == 0: m_used = -inf -> true
-            if (j == 0) {
-                m_used = mx;
-            } else if (__any_sync(0xffffffffu, grow)) {
-                const float m_new = grow ? mx : m_used;
-                const float alpha = ex2_approx((m_used - m_new) * c);
-                l *= alpha;
-                m_used = m_new;
-#pragma unroll
-                for (int c0 = 0; c0 < AT_D; c0 += 16) {
-                    uint32_t o[16];
-                    tmem_ld16(tO + lane_addr + c0, o);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st16(tO + lane_addr + c0, o);
-                }
+            fence_async_smem();
+            named_bar_sync(2, 128);
+            if (warp == 0 && lane == 0) {
+                tma_store_3d(&tmO, so, h * AT_D, q0, b);
+                bulk_commit();
             }
-            const float mc = m_used * c;
-            float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                if (ch * 32 < nv) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float p0 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i]), c, -mc));
-                        float p1 = ex2_approx(fmaf(__uint_as_float(s[ch * 32 + i + 1]), c, -mc));
-                        sum0 += p0;
-                        sum1 += p1;
-                        pk[i >> 1] = pack_bf16(p0, p1);
-                    }
-                    tmem_st16(tP + lane_addr + ch * 16, pk);
-                }
-            }
-            l += sum0 + sum1;
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> bf16 -> smem (the Q tile is dead: every S MMA has completed) -> TMA store
-        mbar_wait(pv_done, (nK - 1) & 1);
-        tc_fence_after();
-        const float inv = 1.0f / l;
-        uint8_t *so = base + AttnFwdSmem::Q;
-#pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 16) {
-            uint32_t o[16];
-            tmem_ld16(tO + lane_addr + c0, o);
-            tmem_wait_ld();
-            uint4 v0, v1;
-            v0.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-            v0.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-            v0.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-            v0.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-            v1.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-            v1.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-            v1.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-            v1.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-            *reinterpret_cast<uint4 *>(so + rowtile_unit(row, c0 / 8)) = v0;
-            *reinterpret_cast<uint4 *>(so + rowtile_unit(row, c0 / 8 + 1)) = v1;
-        }
-        if (q0 + row < N) lse2[(size_t)bh * N + q0 + row] = fmaf(m_used, c, log2f(l));
-        fence_async_smem();
-        tc_fence_before();
-        named_bar_sync(1, 128);
-        if (warp == 4 && lane == 0) {
-            tma_store_3d(&tmO, so, h * AT_D, q0, b);
-            bulk_commit();
-            bulk_wait_read<0>();
-        }
+        if (warp == 0 && lane == 0) bulk_wait<0>();
     }
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc<256>(tmem);
     }
+}
+
+// The last (N mod 128) query rows when they are few (AT_TAIL_MAX): one warp per (batch*head, row) on the CUDA cores --
+// a 1-row tile would cost a full 128-row MMA tile in attn_fwd_kernel (S = 513: 20 % of its work).  Lanes split the keys,
+// each with its own online softmax, merged by shuffles at the end.  Same outputs as the tile kernel (out row, lse2).
+constexpr int AT_TAIL_MAX = 1;
+
+__global__ void __launch_bounds__(128)
+attn_fwd_tail_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out, float *__restrict__ lse2, int B, int N,
+                     int H, int n0 /* first tail row */, float c) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nt = N - n0;
+    if (w >= (long long)B * H * nt) return;
+    const int r = (int)(w % nt);
+    const int bh = (int)(w / nt);
+    const int b = bh / H, h = bh - b * H;
+    const int n = n0 + r;
+    const size_t W = (size_t)3 * H * AT_D;
+    const __nv_bfloat16 *qp = qkv + ((size_t)b * N + n) * W + h * AT_D;
+    float qf[AT_D];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(qp + u * 8);
+        const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(x2[e]);
+            qf[u * 8 + 2 * e] = f.x * c;             // scores directly in the log2 domain
+            qf[u * 8 + 2 * e + 1] = f.y * c;
+        }
+    }
+    float m = -CUDART_INF_F, l = 0.f, o[AT_D];
+#pragma unroll
+    for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+    for (int key = lane; key < N; key += 32) {
+        const __nv_bfloat16 *kp = qkv + ((size_t)b * N + key) * W + (H + h) * AT_D;
+        const __nv_bfloat16 *vp = kp + (size_t)H * AT_D;
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(kp + u * 8);
+            const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(x2[e]);
+                s = fmaf(qf[u * 8 + 2 * e], f.x, s);
+                s = fmaf(qf[u * 8 + 2 * e + 1], f.y, s);
+            }
+        }
+        const float m_new = fmaxf(m, s);
+        const float corr = ex2_approx(m - m_new);      // first key: ex2(-inf) = 0
+        const float p = ex2_approx(s - m_new);
+        l = fmaf(l, corr, p);
+        m = m_new;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(vp + u * 8);
+            const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(x2[e]);
+                o[u * 8 + 2 * e] = fmaf(o[u * 8 + 2 * e], corr, p * f.x);
+                o[u * 8 + 2 * e + 1] = fmaf(o[u * 8 + 2 * e + 1], corr, p * f.y);
+            }
+        }
+    }
+    float M = m;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, off));
+    const float f = (m == -CUDART_INF_F) ? 0.f : ex2_approx(m - M);     // lanes without keys (N < 32) contribute nothing
+    l *= f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = 1.0f / l;
+    float mine0 = 0.f, mine1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < AT_D; ++i) {
+        float x = o[i] * f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if (i == 2 * lane) mine0 = x;
+        if (i == 2 * lane + 1) mine1 = x;
+    }
+    __nv_bfloat16 *op = out + ((size_t)b * N + n) * H * AT_D + h * AT_D;
+    *reinterpret_cast<uint32_t *>(op + 2 * lane) = pack_bf16(mine0 * inv, mine1 * inv);
+    if (lane == 0) lse2[(size_t)bh * N + n] = M + log2f(l);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -300,7 +449,10 @@ static bool get_fwd_maps(const void *qkv, void *out, int B, int N, int H, AttnMa
 // The query tail is cheap (it is the MMA N / K extent, rounded to 16); `scale` is folded into the dK epilogue and the
 // dQ conversion.  dQ is accumulated across the key blocks of a (batch, head) in an fp32 workspace by TMA reduce-add
 // and converted to bf16 into dqkv by attn_dq_convert_kernel.
-// Warps: 0 = TMA producer, 1 = MMA issuer, 4-11 = compute (warp % 4 = TMEM lane quarter, (warp-4)/4 = query half).
+// Warps: 0-7 = compute (warp % 4 = TMEM lane quarter, warp / 4 = query half), 8 = TMA producer, 9 = MMA issuer.
+// The two query halves (64 queries each) are INDEPENDENT pipelines -- own S / dP / P columns, own barriers, own MMAs
+// (N = 64), own dQ drain -- that only share the tensor core and the dQ MMA: while one warpgroup is in its exp2 (MUFU)
+// phase the other is in its dS (FMA) phase, which is what keeps both pipes busy with a single CTA per SM.
 // =====================================================================================================================
 constexpr int AB_THREADS = 384;
 
@@ -331,18 +483,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
     uint64_t *kv_full = bars + 0;
-    uint64_t *q_full = bars + 1;      // [2]
+    uint64_t *q_full = bars + 1;      // [2] stages
     uint64_t *q_empty = bars + 3;     // [2]
-    uint64_t *s_full = bars + 5;
-    uint64_t *s_free = bars + 6;
-    uint64_t *dp_full = bars + 7;
-    uint64_t *p_full = bars + 8;
-    uint64_t *dv_done = bars + 9;
-    uint64_t *ds_full = bars + 10;
-    uint64_t *dq_full = bars + 11;
-    uint64_t *dq_free = bars + 12;
-    uint64_t *dkv_done = bars + 13;
-    uint32_t *tmem_holder = (uint32_t *)(bars + 14);
+    uint64_t *s_full = bars + 5;      // [2] query halves from here on
+    uint64_t *s_free = bars + 7;
+    uint64_t *dp_full = bars + 9;
+    uint64_t *p_full = bars + 11;
+    uint64_t *dv_done = bars + 13;
+    uint64_t *ds_full = bars + 15;
+    uint64_t *dq_full = bars + 17;
+    uint64_t *dq_free = bars + 18;
+    uint64_t *dkv_done = bars + 19;
+    uint32_t *tmem_holder = (uint32_t *)(bars + 20);
     float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [2][128]
     float *s_delta = s_lse + 256;                                // [2][128]
 
@@ -355,28 +507,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (tid == 0) {
         mbar_init(kv_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        mbar_init(s_full, 1);
-        mbar_init(s_free, 8);
-        mbar_init(dp_full, 1);
-        mbar_init(p_full, 8);
-        mbar_init(dv_done, 1);
-        mbar_init(ds_full, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
+            mbar_init(&dp_full[i], 1); mbar_init(&p_full[i], 4);
+            mbar_init(&dv_done[i], 1); mbar_init(&ds_full[i], 4);
+        }
         mbar_init(dq_full, 1);
         mbar_init(dq_free, 8);
         mbar_init(dkv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<512>(tmem_holder);
+    if (warp == 9) tmem_alloc<512>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
     const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tP = tmem + 448;
+    XQ_TR(tid == 0, 16 * 30 + 2);
+    // queries of block i that half hf holds, rounded up to the MMA granularity (0 when the block ends before the half)
+    auto nq_half = [&](int i, int hf) { return max(0, min(64, ((min(AT_BM, N - i * AT_BM) + 15) & ~15) - hf * 64)); };
 
-    if (warp < 4) {
+    // warps 0-3 / 4-7 = compute warpgroups (query halves 0 / 1), warps 8-11 = control (8 = TMA producer, 9 = MMA issuer):
+    // the scheduler favours the higher warp id among eligible warps, so the single-thread MMA issuer is never starved by
+    // the compute warps it shares a sub-partition with (measured: with the issuer as warp 1 it spent ~130 clk per MMA)
+    if (warp >= 8) {
         reg_dec<88>();
-        if (warp == 0 && lane == 0) {
+        if (warp == 8 && lane == 0) {
             // ===== TMA producer =====
             tma_prefetch_desc(&tmQKV);
             tma_prefetch_desc(&tmDO);
@@ -392,73 +549,105 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 bulk_load_1d(s_lse + st * 128, lseP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
                 bulk_load_1d(s_delta + st * 128, deltaP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t ka = smem_u32(base + AttnBwdSmem::K), va = smem_u32(base + AttnBwdSmem::V);
-            auto nqr_of = [&](int i) { return (min(AT_BM, N - i * AT_BM) + 15) & ~15; };
-            auto issue_s = [&](int i) {
-                const uint32_t qa = smem_u32(base + AttnBwdSmem::Q + (i & 1) * AT_TILE);
-                const uint32_t id = idesc_bf16(AT_BN, nqr_of(i), 0, 0);
+        } else if (warp == 9 && lane == 0) {
+            // ===== MMA issuer: the two query halves are independent pipelines that share the tensor core =====
+            // descriptors of the four operand tiles, built once (advancing one is a 64-bit add)
+            const uint64_t kd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::K)), vd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::V));
+            const uint64_t kd_mn = desc_mn_sw128(smem_u32(base + AttnBwdSmem::K), 16384, 1024);
+            const uint64_t qd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::Q)), dd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::DO));
+            const uint64_t qd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::Q), 16384, 1024);
+            const uint64_t dd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DO), 16384, 1024);
+            const uint64_t dsd0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
+            auto issue_s = [&](int i, int hf) {
+                const int n = nq_half(i, hf);
+                if (n == 0) return;
+                const uint64_t qd = desc_adv(qd_k0, (i & 1) * AT_TILE + hf * 8192);
+                const uint32_t id = idesc_bf16(AT_BN, n, 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_k_sw128(ka + k * 32), desc_k_sw128(qa + k * 32), id, k > 0);
-                umma_commit(s_full);
+                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS + hf * 64, desc_adv(kd_k, k * 32), desc_adv(qd, k * 32), id, k > 0);
+                umma_commit(&s_full[hf]);
             };
-            auto issue_dp = [&](int i) {
-                const uint32_t da = smem_u32(base + AttnBwdSmem::DO + (i & 1) * AT_TILE);
-                const uint32_t id = idesc_bf16(AT_BN, nqr_of(i), 0, 0);
+            auto issue_dp = [&](int i, int hf) {
+                const int n = nq_half(i, hf);
+                if (n == 0) return;
+                const uint64_t dd = desc_adv(dd_k0, (i & 1) * AT_TILE + hf * 8192);
+                const uint32_t id = idesc_bf16(AT_BN, n, 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_k_sw128(va + k * 32), desc_k_sw128(da + k * 32), id, k > 0);
-                umma_commit(dp_full);
+                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP + hf * 64, desc_adv(vd_k, k * 32), desc_adv(dd, k * 32), id, k > 0);
+                umma_commit(&dp_full[hf]);
             };
+            const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
+            const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
+            bool dv_started = false, dk_started = false;
+            // per-half completion counters of the barriers this thread waits on (a half with no queries is skipped on both sides)
+            uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0}, n_dsfull[2] = {0, 0};
             mbar_wait(kv_full, 0);
             mbar_wait(&q_full[0], 0);
             tc_fence_after();
-            issue_s(0);
-            issue_dp(0);
-            const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
-            const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
+            issue_s(0, 0);
+            issue_s(0, 1);
+            issue_dp(0, 0);
+            issue_dp(0, 1);
             for (int i = 0; i < nQ; ++i) {
                 const int st = i & 1;
-                const int ks = nqr_of(i) / 16;
-                if (i + 1 < nQ) {
-                    mbar_wait(s_free, i & 1);
-                    mbar_wait(&q_full[st ^ 1], ((i + 1) >> 1) & 1);
-                    tc_fence_after();
-                    issue_s(i + 1);
-                }
-                const uint32_t qa = smem_u32(base + AttnBwdSmem::Q + st * AT_TILE);
-                const uint32_t da = smem_u32(base + AttnBwdSmem::DO + st * AT_TILE);
-                mbar_wait(p_full, i & 1);
-                tc_fence_after();
-                for (int k = 0; k < ks; ++k)       // dV += P^T dO_i : query k-step k lives at P column (k/4)*32 + (k%4)*8
-                    umma_ts(tDV, tP + (k >> 2) * 32 + (k & 3) * 8, desc_mn_sw128(da + k * 2048, 16384, 1024), id_acc, (i | k) != 0);
-                umma_commit(dv_done);
-                mbar_wait(ds_full, i & 1);
-                tc_fence_after();
-                for (int k = 0; k < ks; ++k)       // dK += dS^T Q_i : dS^T (bf16) sits over dP^T at column (k/4)*64 + (k%4)*8
-                    umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_mn_sw128(qa + k * 2048, 16384, 1024), id_acc, (i | k) != 0);
-                umma_commit(&q_empty[st]);         // Q_i / dO_i tiles are dead once dV_i and dK_i retire
-                if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
-                const uint32_t dsa = smem_u32(base + AttnBwdSmem::DS + st * 2 * AT_TILE);
+                const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
+                const bool more = i + 1 < nQ;
+                if (more) { mbar_wait(&q_full[st ^ 1], ((i + 1) >> 1) & 1); }
 #pragma unroll
-                for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile [K = keys, N = d]
-                    umma_ss(tDQ, desc_mn_sw128(dsa + k * 2048, AT_TILE, 1024), desc_mn_sw128(ka + k * 2048, 16384, 1024), id_dq, k > 0);
-                umma_commit(dq_full);
-                if (i + 1 < nQ) issue_dp(i + 1);
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int ks = nq_half(i, hf) / 16;
+                    if (ks > 0) {
+                        mbar_wait(&p_full[hf], n_pfull[hf]++ & 1);
+                        XQ_TR(i < 30, 16 * i + hf);
+                        tc_fence_after();
+                        for (int k = 0; k < ks; ++k) {    // dV += P^T dO : query k-step k of this half
+                            umma_ts(tDV, tP + hf * 32 + k * 8, desc_adv(dd_mn, hf * 8192 + k * 2048), id_acc, dv_started ? 1u : 0u);
+                            dv_started = true;
+                        }
+                        umma_commit(&dv_done[hf]);
+                        mbar_wait(&s_free[hf], n_sfree[hf]++ & 1);      // (arrived before p_full) S of this half is in registers
+                        tc_fence_after();
+                    }
+                    if (more) issue_s(i + 1, hf);
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int ks = nq_half(i, hf) / 16;
+                    mbar_wait(&ds_full[hf], n_dsfull[hf]++ & 1);        // always arrives (an empty half still zero-fills its dS tile)
+                    XQ_TR(i < 30, 16 * i + 2 + hf);
+                    tc_fence_after();
+                    for (int k = 0; k < ks; ++k) {        // dK += dS^T Q : dS^T (bf16) sits over this half's dP^T columns
+                        umma_ts(tDK, tDP + hf * 64 + k * 8, desc_adv(qd_mn, hf * 8192 + k * 2048), id_acc, dk_started ? 1u : 0u);
+                        dk_started = true;
+                    }
+                    if (hf == 1) {
+                        umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
+                        if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
+                        const uint64_t dsd = desc_adv(dsd0, st * 2 * AT_TILE);
+#pragma unroll
+                        for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
+                            umma_ss(tDQ, desc_adv(dsd, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
+                        umma_commit(dq_full);
+                        XQ_TR(i < 30, 16 * i + 4);
+                    }
+                    if (more) issue_dp(i + 1, hf);
+                }
             }
             umma_commit(dkv_done);
         }
     } else {
         reg_inc<208>();
-        // ===== compute: thread = (key lane, query half) =====
+        // ===== compute: thread = (key lane, query half); the two halves run as independent warpgroups =====
         const int qd = warp & 3;                     // TMEM lane quarter
-        const int hf = (warp - 4) >> 2;              // query half: columns [hf*64, hf*64+64)
+        const int hf = warp >> 2;                    // query half: columns [hf*64, hf*64+64)
         const int krow = qd * 32 + lane;             // key row inside the block
         const bool key_ok = k0 + krow < N;
+        const bool keys_full = k0 + AT_BN <= N;      // warp-uniform: no key of this block needs masking
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        const int ctid = tid - 128;                  // 0..255
+        const int wtid = tid & 127;                  // thread index inside the warpgroup
+        uint32_t n_sfull = 0, n_dpfull = 0, n_dvdone = 0;
         auto drain_dq = [&](int i) {
-            // dQ_i partial (TMEM lanes = queries) -> fp32 smem row tiles -> TMA reduce-add into the accumulator
+            // this warpgroup's 32 head-dim columns of dQ_i (TMEM lanes = queries) -> fp32 smem row tile -> TMA reduce-add
             mbar_wait(dq_full, i & 1);
             tc_fence_after();
             uint32_t r[32];
@@ -467,26 +656,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dq_free);
-            if (ctid == 0) bulk_wait_read<0>();      // the previous reduce has finished reading the staging tiles
-            named_bar_sync(2, 256);
+            if (wtid == 0) bulk_wait_read<0>();      // this warpgroup's previous reduce has finished reading its staging tile
+            named_bar_sync(2 + hf, 128);
             uint8_t *dst = base + AttnBwdSmem::DQ + hf * AT_TILE;
+            const uint32_t dst_a = smem_u32(dst);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                *reinterpret_cast<uint4 *>(dst + rowtile_unit(krow, u)) = make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+            for (int u = 0; u < 8; ++u) sts128(dst_a + rowtile_unit(krow, u), make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]));
             fence_async_smem();
-            named_bar_sync(3, 256);
-            if (ctid == 0) {
-                tma_reduce_add_3d(&tmDQ, base + AttnBwdSmem::DQ, 0, i * AT_BM, bh);
-                tma_reduce_add_3d(&tmDQ, base + AttnBwdSmem::DQ + AT_TILE, 32, i * AT_BM, bh);
+            named_bar_sync(4 + hf, 128);
+            if (wtid == 0) {
+#ifndef XQ_ATTN_EXP_NODQ      // experiment switch (tools/): time the kernel without the dQ reduce traffic
+                tma_reduce_add_3d(&tmDQ, dst, hf * 32, i * AT_BM, bh);
+#endif
                 bulk_commit();
             }
         };
         for (int i = 0; i < nQ; ++i) {
             const int st = i & 1;
-            const int nqr = (min(AT_BM, N - i * AT_BM) + 15) & ~15;
-            const int ncol = max(0, min(64, nqr - hf * 64));        // columns of this half the MMAs produced
+            const int ncol = nq_half(i, hf);                        // columns of this half the MMAs produce
             mbar_wait(&q_full[st], (i >> 1) & 1);                   // statistics of this query block are in smem
-            mbar_wait(s_full, i & 1);
+            const uint32_t dsrow = smem_u32(base + AttnBwdSmem::DS + st * 2 * AT_TILE + hf * AT_TILE);
+            if (ncol == 0) {
+                // no query of this block falls in this half: its dS tile must still read as zero for the dQ MMA
+                if (i > 0) drain_dq(i - 1);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sts128(dsrow + rowtile_unit(krow, u), make_uint4(0u, 0u, 0u, 0u));
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ds_full[hf]);
+                continue;
+            }
+            mbar_wait(&s_full[hf], n_sfull++ & 1);
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 6 + 5 * hf);
             tc_fence_after();
             float p[64];
 #pragma unroll
@@ -495,22 +696,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);
-            const float4 *l4 = reinterpret_cast<const float4 *>(s_lse + st * 128 + hf * 64);
+            if (lane == 0) mbar_arrive(&s_free[hf]);
+            const uint32_t l4 = smem_u32(s_lse + st * 128 + hf * 64);
+            if (keys_full && ncol == 64) {
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
+                for (int g = 0; g < 16; ++g) {
+                    const float4 L = lds128f(l4 + g * 16);
+                    p[4 * g + 0] = ex2_approx(fmaf(p[4 * g + 0], c, -L.x));
+                    p[4 * g + 1] = ex2_approx(fmaf(p[4 * g + 1], c, -L.y));
+                    p[4 * g + 2] = ex2_approx(fmaf(p[4 * g + 2], c, -L.z));
+                    p[4 * g + 3] = ex2_approx(fmaf(p[4 * g + 3], c, -L.w));
+                }
+            } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 L = l4[ch * 4 + g];
-                    const int o = ch * 16 + g * 4;
-                    const bool ok = key_ok && (ch * 16 < ncol);
-                    p[o + 0] = ok ? ex2_approx(fmaf(p[o + 0], c, -L.x)) : 0.f;
-                    p[o + 1] = ok ? ex2_approx(fmaf(p[o + 1], c, -L.y)) : 0.f;
-                    p[o + 2] = ok ? ex2_approx(fmaf(p[o + 2], c, -L.z)) : 0.f;
-                    p[o + 3] = ok ? ex2_approx(fmaf(p[o + 3], c, -L.w)) : 0.f;
+                for (int g = 0; g < 16; ++g) {
+                    const float4 L = lds128f(l4 + g * 16);
+                    const bool ok = key_ok && ((g >> 2) * 16 < ncol);
+                    p[4 * g + 0] = ok ? ex2_approx(fmaf(p[4 * g + 0], c, -L.x)) : 0.f;
+                    p[4 * g + 1] = ok ? ex2_approx(fmaf(p[4 * g + 1], c, -L.y)) : 0.f;
+                    p[4 * g + 2] = ok ? ex2_approx(fmaf(p[4 * g + 2], c, -L.z)) : 0.f;
+                    p[4 * g + 3] = ok ? ex2_approx(fmaf(p[4 * g + 3], c, -L.w)) : 0.f;
                 }
             }
-            if (i > 0) { mbar_wait(dv_done, (i - 1) & 1); tc_fence_after(); }      // the P buffer is free
+            if (n_dvdone < n_sfull - 1) { mbar_wait(&dv_done[hf], n_dvdone++ & 1); tc_fence_after(); }   // the P buffer of this half is free
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 uint32_t pk[16];
@@ -521,12 +729,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(&p_full[hf]);
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 7 + 5 * hf);
             if (i > 0) drain_dq(i - 1);
-            mbar_wait(dp_full, i & 1);
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 8 + 5 * hf);
+            mbar_wait(&dp_full[hf], n_dpfull++ & 1);
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 9 + 5 * hf);
             tc_fence_after();
-            const float4 *d4 = reinterpret_cast<const float4 *>(s_delta + st * 128 + hf * 64);
-            uint8_t *dsrow = base + AttnBwdSmem::DS + st * 2 * AT_TILE + hf * AT_TILE;
+            const uint32_t d4 = smem_u32(s_delta + st * 128 + hf * 64);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t dp[16], pk[8];
@@ -539,7 +749,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const float4 Dl = d4[ch * 4 + g];
+                    const float4 Dl = lds128f(d4 + (ch * 4 + g) * 16);
                     const int o = ch * 16 + g * 4;
                     const float d0 = p[o + 0] * (__uint_as_float(dp[g * 4 + 0]) - Dl.x);
                     const float d1 = p[o + 1] * (__uint_as_float(dp[g * 4 + 1]) - Dl.y);
@@ -549,26 +759,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     pk[g * 2 + 1] = pack_bf16(d2, d3);
                 }
                 // dS^T for the dK MMA (TMEM, over this thread's own dP^T columns) ...
-                {
-                    uint32_t lo[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) lo[e] = pk[e];
-                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
-                                 ::"r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]),
-                                   "r"(tDP + lane_addr + hf * 64 + ch * 8)
-                                 : "memory");
-                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                             ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
+                               "r"(tDP + lane_addr + hf * 64 + ch * 8)
+                             : "memory");
                 // ... and dS for the dQ MMA (smem, MN-major: row = key, 64 queries of this half along the row)
-                *reinterpret_cast<uint4 *>(dsrow + rowtile_unit(krow, ch * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4 *>(dsrow + rowtile_unit(krow, ch * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                sts128(dsrow + rowtile_unit(krow, ch * 2), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                sts128(dsrow + rowtile_unit(krow, ch * 2 + 1), make_uint4(pk[4], pk[5], pk[6], pk[7]));
             }
             fence_async_smem();
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(ds_full);
+            if (lane == 0) mbar_arrive(&ds_full[hf]);
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 10 + 5 * hf);
         }
         drain_dq(nQ - 1);
+        XQ_TR(qd == 0 && lane == 0, 16 * 30 + hf);
         // ---- epilogue: dV (query half 0's warps) and dK * scale (half 1's warps) -> bf16 -> smem -> TMA store
         mbar_wait(dkv_done, 0);
         tc_fence_after();
@@ -576,6 +783,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const uint32_t src = hf == 0 ? tDV : tDK;
             const float mul = hf == 0 ? 1.0f : scale;
             uint8_t *so = base + AttnBwdSmem::Q + hf * AT_TILE;      // both Q stages are dead
+            const uint32_t so_a = smem_u32(so);
 #pragma unroll
             for (int c0 = 0; c0 < AT_D; c0 += 16) {
                 uint32_t o[16];
@@ -590,21 +798,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 v1.y = pack_bf16(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
                 v1.z = pack_bf16(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
                 v1.w = pack_bf16(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
-                *reinterpret_cast<uint4 *>(so + rowtile_unit(krow, c0 / 8)) = v0;
-                *reinterpret_cast<uint4 *>(so + rowtile_unit(krow, c0 / 8 + 1)) = v1;
+                sts128(so_a + rowtile_unit(krow, c0 / 8), v0);
+                sts128(so_a + rowtile_unit(krow, c0 / 8 + 1), v1);
             }
             fence_async_smem();
             tc_fence_before();
-            named_bar_sync(4 + hf, 128);
-            if ((ctid & 127) == 0) {
+            named_bar_sync(6 + hf, 128);
+            if (wtid == 0) {
                 tma_store_3d(&tmDQKV, so, hf == 0 ? colV : colK, k0, b);
                 bulk_commit();
+                bulk_wait<0>();          // this warpgroup's reduce-adds and its store complete before the CTA retires
             }
-            if (ctid == 0 || ctid == 128) bulk_wait<0>();    // reduce-adds (ctid 0) and stores complete before the CTA retires
         }
     }
     __syncthreads();
-    if (warp == 1) {
+    XQ_TR(tid == 0, 16 * 30 + 3);
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
@@ -711,6 +920,13 @@ static size_t attn_bwd_ws_layout(int B, int N, int H, size_t *off_lse, size_t *o
 
 extern "C" {
 
+#ifdef XQ_ATTN_TRACE
+int xq_dev_set_attn_trace(void *dev_ptr) {
+    long long *p = (long long *)dev_ptr;
+    return cudaMemcpyToSymbol(xq::g_attn_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H) {
     if (B <= 0 || N <= 0 || H <= 0) return 0;
     return xq::attn_bwd_ws_layout(B, N, H, nullptr, nullptr);
@@ -773,17 +989,31 @@ int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H
     if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) return XQ_ERR_ARG;
     AttnMaps m;
     if (!get_fwd_maps(qkv, out, B, N, H, m)) return XQ_ERR_UNSUPPORTED;
-    const int nQ = (N + AT_BM - 1) / AT_BM;
+    // query tiles: full 128-row tiles on the tensor cores; a short remainder (<= AT_TAIL_MAX rows) on the CUDA cores
+    const int n_tail = (N % AT_BM != 0 && N % AT_BM <= AT_TAIL_MAX && N > AT_BM) ? N % AT_BM : 0;
+    const int nQ = n_tail ? N / AT_BM : (N + AT_BM - 1) / AT_BM;
     const size_t smem = AttnFwdSmem::BYTES + 1024;
     static bool attr_set = false;
+    static int n_sm = 0;
     if (!attr_set) {
         XQ_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        XQ_CUDA_TRY(cudaGetDevice(&dev));
+        XQ_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
-    const long long ctas = (long long)B * H * nQ;
-    if (ctas > 0x7fffffffLL) return XQ_ERR_ARG;
-    attn_fwd_kernel<<<(unsigned)ctas, AT_THREADS, smem, (cudaStream_t)stream>>>(m.tmQKV, m.tmO, lse2, N, H, nQ, scale * 1.4426950408889634f);
+    const long long tiles = (long long)B * H * nQ;
+    if (tiles > 0x7fffffffLL) return XQ_ERR_ARG;
+    const int grid = (int)(tiles < 2LL * n_sm ? tiles : 2LL * n_sm);
+    const float c = scale * 1.4426950408889634f;
+    attn_fwd_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(m.tmQKV, m.tmO, lse2, N, H, nQ, (int)tiles, c);
     XQ_LAUNCH_CHECK("attn_fwd_kernel");
+    if (n_tail) {
+        const long long warps = (long long)B * H * n_tail;
+        attn_fwd_tail_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, lse2, B, N, H, N - n_tail, c);
+        XQ_LAUNCH_CHECK("attn_fwd_tail_kernel");
+    }
     return XQ_OK;
 }
 

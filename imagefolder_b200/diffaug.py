@@ -56,7 +56,9 @@ class DiffAug(object):
             return BCHW
         B, _, H, W = BCHW.shape
         rand01 = torch.rand(7, B, 1, 1, device=BCHW.device)                 # device generator (:64)
-        flags = int(trans) | (int(color) << 1) | (int(bool(self.using_cutout and cut)) << 2)
+        cut_h, cut_w = round(H * self.cutout), round(W * self.cutout)
+        # a zero-sized cutout is an empty index grid in the reference (diffaug.py:100-112: nothing is zeroed)
+        flags = int(trans) | (int(color) << 1) | (int(bool(self.using_cutout and cut and cut_h > 0 and cut_w > 0)) << 2)
         if flags == 0:
             return BCHW
-        return loss_ops.diffaug_apply(BCHW, rand01.view(7, B), flags, round(H * self.cutout), round(W * self.cutout))
+        return loss_ops.diffaug_apply(BCHW, rand01.view(7, B), flags, cut_h, cut_w)

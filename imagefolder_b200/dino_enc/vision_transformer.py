@@ -169,9 +169,9 @@ class VisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=0, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4.0, qkv_bias=True, init_values=None, class_token=True, no_embed_class=False, reg_tokens=0,
                  pre_norm=False, drop_path_rate=0.0, attn_layer=Attention, num_latent_tokens=32, global_pool='token',
-                 **unused):
+                 norm_eps=1e-6, **unused):
         super().__init__()
-        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        norm_layer = partial(nn.LayerNorm, eps=norm_eps)     # timm: 1e-6 for the DINOv2 / plain ViTs, 1e-5 for the CLIP variants
         self.num_classes = num_classes
         self.global_pool = global_pool
         self.num_features = self.embed_dim = embed_dim
@@ -267,14 +267,61 @@ _ARCH = {
 }
 
 
+# timm builds its CLIP variants with norm_layer=nn.LayerNorm (eps 1e-5); the DINOv2 ones with eps 1e-6
+_NORM_EPS = {'vit_base_patch16_clip_224.openai': 1e-5}
+
+
+def _resample_checkpoint(state, model):
+    """timm's checkpoint_filter_fn for the two tensors whose shape depends on (img_size, patch_size):
+    pos_embed (bicubic, antialias, prefix tokens kept) and patch_embed.proj.weight (bicubic resize of the kernel)."""
+    out = dict(state)
+    pe = out.get('pos_embed')
+    if pe is not None and pe.shape != model.pos_embed.shape:
+        npt = 0 if model.no_embed_class else model.num_prefix_tokens
+        out['pos_embed'] = resample_abs_pos_embed(pe, model.patch_embed.grid_size, num_prefix_tokens=npt)
+    w = out.get('patch_embed.proj.weight')
+    if w is not None and w.shape != model.patch_embed.proj.weight.shape:
+        out['patch_embed.proj.weight'] = F.interpolate(w.float(), size=model.patch_embed.proj.weight.shape[-2:],
+                                                       mode='bicubic', antialias=True, align_corners=False).to(w.dtype)
+    return out
+
+
 def create_model(model_name: str, pretrained: bool = False, **kwargs) -> VisionTransformer:
-    """stand-in for timm.models.create_model for the names the reference uses.  There is no network
-    here, so `pretrained=True` only records the request: weights are whatever the caller loads
-    afterwards (checkpoint keys match timm's)."""
+    """stand-in for timm.models.create_model for the names the reference uses.  There is no network here:
+    `pretrained=True` loads a LOCAL timm-format checkpoint named by the environment variable
+    XQ_TIMM_CKPT_<NAME> (NAME = model name upper-cased, non-alphanumerics -> '_'; e.g.
+    XQ_TIMM_CKPT_VIT_BASE_PATCH14_DINOV2_LVD142M), resampling pos_embed / patch_embed to the requested geometry the way
+    timm's checkpoint filter does (37x37 -> 16x16, patch 14 -> 16 for the reference's 256px / patch-16 models).  Without
+    that file the weights stay at their random initialisation and this is said LOUDLY (warning, or an exception with
+    XQ_REQUIRE_PRETRAINED=1): a frozen `semantic_guide` / `detail_guide` teacher on random weights regresses noise --
+    configure those guides as 'none' unless their checkpoints are present."""
+    import os
+    import re
+    import warnings
     if model_name not in _ARCH:
         raise RuntimeError(f"Unknown model ({model_name})")
     args = dict(_ARCH[model_name])
     args.update(kwargs)
+    if model_name in _NORM_EPS:
+        args.setdefault('norm_eps', _NORM_EPS[model_name])
     model = VisionTransformer(**args)
     model.pretrained_requested = bool(pretrained)
+    model.pretrained_loaded = False
+    if pretrained:
+        env = "XQ_TIMM_CKPT_" + re.sub(r"[^A-Za-z0-9]", "_", model_name).upper()
+        path = os.environ.get(env, "")
+        if path and os.path.exists(path):
+            state = torch.load(path, map_location="cpu")
+            state = state.get("state_dict", state.get("model", state))
+            res = model.load_state_dict(_resample_checkpoint(state, model), strict=False)
+            bad = [k for k in res.missing_keys if not k.startswith('head')]
+            if bad:
+                raise RuntimeError(f"{path}: not a timm checkpoint of {model_name} (missing {bad[:4]})")
+            model.pretrained_loaded = True
+        else:
+            msg = (f"create_model({model_name!r}, pretrained=True): no local checkpoint ({env} is unset or missing); "
+                   "the model keeps its RANDOM initialisation")
+            if os.environ.get("XQ_REQUIRE_PRETRAINED", "0") == "1":
+                raise RuntimeError(msg)
+            warnings.warn(msg)
     return model

@@ -206,7 +206,13 @@ class DinoDisc(nn.Module):
                 if '.attn.qkv.bias' in k:                      # the reference zeroes the key bias (:166-170)
                     c = state[k].numel() // 3
                     state[k][c:2 * c].zero_()
-            backbone.load_state_dict(state, strict=False)
+            res = backbone.load_state_dict(state, strict=False)
+            # the reference's own check (discriminator_dino.py:171-175): only the input-normalisation buffers may be
+            # absent from the file, and nothing may be left over -- a wrapped / prefixed checkpoint must not pass silently
+            missing = [k for k in res.missing_keys if not k.startswith(('x_scale', 'x_shift'))]
+            if missing or res.unexpected_keys:
+                raise RuntimeError(f"DinoDisc: {ckpt} does not match the frozen DINO ViT-S/16 backbone "
+                                   f"(missing {missing[:4]}, unexpected {list(res.unexpected_keys)[:4]})")
         else:
             warnings.warn("DinoDisc: no DINO ViT-S/16 checkpoint found (set XQ_DINO_CKPT); the frozen backbone is RANDOM")
         if device == 'cuda' and not torch.cuda.is_available():

@@ -1,7 +1,7 @@
 """LPIPS perceptual loss (VGG16) -- tokenizer/tokenizer_image/lpips.py:52-159.
 
 Checkpoint-compatible with the reference (`scaling_layer.{shift,scale}`, `net.slice{1..5}.{i}.{weight,bias}`,
-`lin{0..4}.model.1.weight`), so `vgg.pth` loads unchanged.  The VGG16 trunk is a stack of library convolutions; what the
+`lin{0..4}.model.1.weight`); `vgg.pth` carries the lin layers only (see load_from_pretrained).  The VGG16 trunk is a stack of library convolutions; what the
 reference does AFTER the trunk -- per stage: channel-normalise both maps, subtract, square, 1x1 `lin` conv, spatial mean,
 i.e. ~10 full passes over feature maps of up to 2 GB -- is one fused CUDA pass per stage (xq_lpips_layer_forward /
 _backward, csrc/loss_kernels.cu).
@@ -11,8 +11,10 @@ silent substitute.  Two situations keep the reference's op sequence on library k
 front of the `lin` conv (a semantic the fused kernel does not have; `VQLoss` keeps LPIPS in eval mode), and CPU tensors,
 where the whole module -- trunk included -- is a plain library network.
 
-There is no network here: `load_from_pretrained` reads `<this dir>/cache/vgg.pth` (the reference's cache location,
-lpips.py:67-69) or `$XQ_LPIPS_CKPT` when present and otherwise leaves the random initialisation in place with a warning.
+There is no network here.  The reference takes the trunk from torchvision (`models.vgg16(pretrained=True)`) and only the
+`lin` layers from vgg.pth; `load_from_pretrained` mirrors that with two local files ($XQ_VGG16_CKPT for the trunk,
+$XQ_LPIPS_CKPT or `<this dir>/cache/vgg.pth` for the lin layers), reports every tensor that is still at its random
+initialisation (`self.unloaded_keys`, a warning -- or an exception with XQ_REQUIRE_PRETRAINED=1).
 """
 from __future__ import annotations
 
@@ -108,13 +110,55 @@ class LPIPS(nn.Module):
             p.requires_grad = False
 
     def load_from_pretrained(self, name="vgg_lpips"):
-        cands = [os.environ.get("XQ_LPIPS_CKPT", ""), os.path.join(os.path.dirname(os.path.abspath(__file__)), "cache", "vgg.pth")]
-        for path in cands:
+        """Two files, as in the reference: the torchvision VGG16 trunk (`models.vgg16(pretrained=True)`, lpips.py:119)
+        and vgg.pth, which carries ONLY the `lin{k}.model.1.weight` 1x1 convs (which is why the reference loads it with
+        strict=False, lpips.py:72).  There is no network here, so both come from local files:
+            $XQ_VGG16_CKPT   torchvision vgg16 state_dict (`features.N.{weight,bias}`), remapped to `net.slice{k}.N.*`
+            $XQ_LPIPS_CKPT   vgg.pth (or <this dir>/cache/vgg.pth, the reference's cache location)
+        A checkpoint that already holds `net.slice*` keys (a full LPIPS state_dict) serves both.  Whatever is still
+        unset afterwards is reported loudly: a perceptual loss on a random trunk is not a perceptual loss."""
+        loaded = set()
+        own = self.state_dict()
+        trunk = os.environ.get("XQ_VGG16_CKPT", "")
+        if trunk and os.path.exists(trunk):
+            sd = torch.load(trunk, map_location="cpu")
+            sd = sd.get("state_dict", sd)
+            remap = {}
+            for k, v in sd.items():
+                if k.startswith("features."):
+                    idx = int(k.split(".")[1])
+                    if idx < _SLICE_ENDS[-1]:
+                        si = next(i for i, e in enumerate(_SLICE_ENDS, 1) if idx < e)
+                        remap[f"net.slice{si}.{idx}.{k.split('.')[2]}"] = v
+            bad = [k for k, v in remap.items() if k not in own or own[k].shape != v.shape]
+            if bad:
+                raise RuntimeError(f"LPIPS: {trunk} is not a torchvision vgg16 state_dict (unexpected {bad[:3]})")
+            self.load_state_dict(remap, strict=False)
+            loaded |= set(remap)
+        used = None
+        for path in (os.environ.get("XQ_LPIPS_CKPT", ""), os.path.join(os.path.dirname(os.path.abspath(__file__)), "cache", "vgg.pth")):
             if path and os.path.exists(path):
-                self.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
-                return path
-        warnings.warn("LPIPS: no vgg.pth found (set XQ_LPIPS_CKPT); the perceptual loss runs on RANDOM weights")
-        return None
+                sd = torch.load(path, map_location="cpu")
+                res = self.load_state_dict(sd, strict=False)
+                if res.unexpected_keys:
+                    raise RuntimeError(f"LPIPS: unexpected keys in {path}: {res.unexpected_keys[:4]}")
+                loaded |= set(sd)
+                used = path
+                break
+        missing = [k for k in own if k not in loaded and not k.startswith("scaling_layer.")]
+        self.unloaded_keys = missing
+        if missing:
+            trunk_missing = [k for k in missing if k.startswith("net.")]
+            lin_missing = [k for k in missing if k.startswith("lin")]
+            msg = "LPIPS runs on RANDOM weights for: "
+            if trunk_missing:
+                msg += f"the VGG16 trunk ({len(trunk_missing)} tensors; set XQ_VGG16_CKPT to a torchvision vgg16 state_dict) "
+            if lin_missing:
+                msg += f"the lin layers ({len(lin_missing)} tensors; set XQ_LPIPS_CKPT to vgg.pth)"
+            if os.environ.get("XQ_REQUIRE_PRETRAINED", "0") == "1":
+                raise RuntimeError(msg)
+            warnings.warn(msg)
+        return used
 
     def _stage(self, i, f0, f1):
         lin = getattr(self, f"lin{i}").model[-1]

@@ -24,7 +24,7 @@ def _ref(qkv32, H):
 
 @pytest.mark.parametrize("B,N,H", [(2, 513, 3), (2, 514, 2), (1, 769, 2), (2, 499, 2), (2, 379, 3), (3, 1, 1), (1, 16, 2),
                                    (2, 128, 2), (2, 129, 1), (1, 1024, 1), (1, 333, 12)])
-@pytest.mark.parametrize("amp", [1.0, 4.0])
+@pytest.mark.parametrize("amp", [1.0, 2.5])
 def test_attention_forward_backward_match_fp32_reference(B, N, H, amp):
     from imagefolder_b200 import vit_ops
     torch.manual_seed(N * 7 + H)

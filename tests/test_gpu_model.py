@@ -47,7 +47,22 @@ def test_forward_matches_oracle_fp32(name):
                 idx_ref = xo.vq_forward(hb.numpy(), npy(qm.embedding.weight))["idx"]
                 np.testing.assert_array_equal(npy(qm.last_idx), idx_ref)
             else:
+                # every scale's indices, recomputed by the oracle ON THE SAME GPU LATENT of this branch
                 assert len(qm.last_idx_Bl) == SN
+                pn = list(cfg["v_patch_nums"])
+                mods = qm.quant_resi.modules_list()
+                pw = np.stack([npy(m.weight) for m in mods])
+                pb = np.stack([npy(m.bias) for m in mods])
+                hbn = np.ascontiguousarray(hb.numpy())
+                if name.startswith("MSBR"):
+                    fw = xo.lfq_forward(hbn, pw, pb, pn, using_znorm=cfg.get("codebook_l2_norm", True),
+                                        codebook_drop=cfg.get("codebook_drop", 0.0), dropout=dr, scaler=npy(qm.scaler),
+                                        entropy_weight=cfg.get("entropy_weight", 0.0))
+                else:
+                    fw = xo.vq2_forward(hbn, npy(qm.embedding.weight), pw, pb, pn, using_znorm=True,
+                                        codebook_drop=cfg.get("codebook_drop", 0.0), dropout=dr)
+                for si in range(SN):
+                    np.testing.assert_array_equal(npy(qm.last_idx_Bl[si]).astype(np.int64), np.asarray(fw["idx"][si]))
         np.testing.assert_allclose(float(vq), float(vq_r), rtol=1e-3)
         np.testing.assert_allclose(float(commit), float(cm_r), rtol=1e-3)
         np.testing.assert_allclose(float(ent), float(en_r), rtol=1e-3, atol=1e-6)

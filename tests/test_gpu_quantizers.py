@@ -573,3 +573,59 @@ def test_var_helpers_consistent_with_token_decode_and_errors():
     assert rv is fv
     close(r32, npy(rv))
     close(n32, npy(nv))
+
+
+# ------------------------------------------------------------------------------------------
+# round 2: reference goldens at the BASELINE codebook sizes, and the unscreened multi-scale seed
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vq8192_c32", "vq16384_c32"])
+def test_vq_baseline_shaped_reference_goldens(name):
+    """V = 8192 / 16384, C = 32 (BASELINE configs #2 / #3): indices bit-exact against the REFERENCE's own output
+    (tests/golden/make_golden.py --round2-only), on both the tcgen05 path and the exact CUDA-core path."""
+    import os
+    from test_oracle_golden import big_vq_inputs
+    g = load_golden(name)
+    E, z, g_out = big_vq_inputs(g)
+    for algo in ("auto", "exact"):
+        os.environ["XQ_VQ_ALGO"] = algo
+        try:
+            q = make_vq(E)
+            zt = dev(z, grad=True)
+            out, usage, vq, commit, _ = q(zt, ret_usages=True)
+            np.testing.assert_array_equal(npy(q.last_idx).reshape(-1), g["idx"].reshape(-1).astype(np.int64))
+            close(out[:, :, ::2, ::2], g["out_sub"])
+            close(vq, g["vq"])
+            close(commit, g["commit"])
+            ((out * dev(g_out)).sum() + float(g["w_vq"]) * vq + float(g["w_commit"]) * commit).backward()
+            close(zt.grad[:, :, ::2, ::2], g["gz_sub"])
+            gE_ref = np.zeros(E.shape, np.float32)
+            gE_ref[g["gE_rows"]] = g["gE_vals"]
+            close(q.embedding.weight.grad, gE_ref)
+        finally:
+            os.environ.pop("XQ_VQ_ALGO", None)
+
+
+def test_msvr_unscreened_seed_counts_mismatches_on_gpu():
+    """The reference's indices on a seed that was NOT screened for near-ties: count the CUDA path's mismatches and
+    require each first divergence to be a near-tie (top-2 margin < 1e-5, margins from the oracle on the same inputs)."""
+    from imagefolder_b200 import VectorQuantizer2
+    from test_oracle_golden import count_first_divergences, msvr_unscreened_inputs
+    g = load_golden("msvr_unscreened")
+    E, phi_w, phi_b, f, pn = msvr_unscreened_inputs(g)
+    V, C = E.shape
+    q = VectorQuantizer2(V, C, using_znorm=True, v_patch_nums=pn, num_latent_tokens=pn[-1] ** 2, share_quant_resi=4,
+                         codebook_drop=0.0).cuda().eval()
+    q.embedding.weight.data.copy_(dev(E))
+    for i, m in enumerate(q.quant_resi.modules_list()):
+        m.weight.data.copy_(dev(phi_w[i]))
+        m.bias.data.copy_(dev(phi_b[i]))
+    with torch.no_grad():
+        idx = [npy(t) for t in q.f_to_idxBl_or_fhat(dev(f), to_fhat=False, v_patch_nums=pn)]
+        fhat = q.f_to_idxBl_or_fhat(dev(f), to_fhat=True, v_patch_nums=pn)[-1]
+    fw = xo.vq2_forward(f, E, phi_w, phi_b, pn, using_znorm=True)
+    ref = [g[f"idx{si}"] for si in range(len(pn))]
+    diverged, tokens = count_first_divergences(idx, ref, fw["margins"], f.shape[0])
+    print("msvr_unscreened (GPU): samples diverged", diverged, "tokens", tokens)
+    assert diverged <= 1
+    if diverged == 0:
+        close(fhat[:, :, ::2, ::2], g["fhat_sub"])

@@ -145,3 +145,68 @@ def test_stylegan_discriminator_layout_and_blur():
     x = torch.rand(2, 3, 32, 32) * 2 - 1
     cb = (torch.tensor(0.1), torch.tensor(0.1), torch.tensor(0.0), [1.0])
     assert torch.isfinite(loss(cb, None, None, None, x, x * 0.9, 0, 1)) and torch.isfinite(loss(cb, None, None, None, x, x * 0.9, 1, 1))
+
+
+# ---- round 2: pretrained-weight plumbing is explicit and loud ------------------------------------
+def test_lpips_reports_a_random_trunk_and_loads_torchvision_layout(tmp_path, monkeypatch):
+    import warnings
+    import torch
+    from imagefolder_b200.lpips import LPIPS
+    monkeypatch.delenv("XQ_VGG16_CKPT", raising=False)
+    monkeypatch.delenv("XQ_LPIPS_CKPT", raising=False)
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        ref = LPIPS().eval()
+    lin_only = {k: v.clone() for k, v in ref.state_dict().items() if k.startswith("lin")}       # what vgg.pth carries
+    torch.save(lin_only, tmp_path / "vgg.pth")
+    monkeypatch.setenv("XQ_LPIPS_CKPT", str(tmp_path / "vgg.pth"))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = LPIPS().eval()
+    assert any("VGG16 trunk" in str(x.message) for x in w)                   # lin-only file: the trunk is random, said loudly
+    assert m.unloaded_keys and all(k.startswith("net.") for k in m.unloaded_keys)
+    assert torch.equal(m.lin0.model[-1].weight, ref.lin0.model[-1].weight)
+    monkeypatch.setenv("XQ_REQUIRE_PRETRAINED", "1")
+    with pytest.raises(RuntimeError):
+        LPIPS()
+    monkeypatch.delenv("XQ_REQUIRE_PRETRAINED")
+    # torchvision layout: features.N.{weight,bias}
+    tv = {}
+    for k, v in ref.state_dict().items():
+        if k.startswith("net.slice"):
+            _, _, idx, leaf = k.split(".")
+            tv[f"features.{idx}.{leaf}"] = v.clone()
+    tv["classifier.0.weight"] = torch.zeros(4, 4)                            # ignored, as in the full torchvision file
+    torch.save(tv, tmp_path / "vgg16.pth")
+    monkeypatch.setenv("XQ_VGG16_CKPT", str(tmp_path / "vgg16.pth"))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m2 = LPIPS().eval()
+    assert m2.unloaded_keys == [] and not w
+    for k, v in ref.state_dict().items():
+        assert torch.equal(m2.state_dict()[k], v), k
+
+
+def test_create_model_pretrained_is_loud_and_resamples_local_checkpoints(tmp_path, monkeypatch):
+    import warnings
+    import torch
+    from imagefolder_b200.dino_enc.vision_transformer import create_model
+    name = "vit_small_patch14_dinov2.lvd142m"
+    env = "XQ_TIMM_CKPT_VIT_SMALL_PATCH14_DINOV2_LVD142M"
+    monkeypatch.delenv(env, raising=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = create_model(name, pretrained=True, img_size=64, patch_size=16, depth=1)
+    assert any("RANDOM" in str(x.message) for x in w) and not m.pretrained_loaded
+    # a "timm" checkpoint at the native geometry (here 56px / patch 14 -> 4x4 grid) loads into 64px / patch 16
+    torch.manual_seed(0)
+    src = create_model(name, pretrained=False, img_size=56, patch_size=14, depth=1)
+    torch.save(src.state_dict(), tmp_path / "vit.pth")
+    monkeypatch.setenv(env, str(tmp_path / "vit.pth"))
+    dst = create_model(name, pretrained=True, img_size=64, patch_size=16, depth=1)
+    assert dst.pretrained_loaded
+    assert dst.pos_embed.shape == (1, 17, 384) and dst.patch_embed.proj.weight.shape[-1] == 16
+    assert torch.equal(dst.blocks[0].attn.qkv.weight, src.blocks[0].attn.qkv.weight)
+    assert torch.allclose(dst.pos_embed[:, :1], src.pos_embed[:, :1])         # the class-token position is kept as is
+    clip = create_model("vit_base_patch16_clip_224.openai", pretrained=False, depth=1)
+    assert clip.norm.eps == 1e-5 and src.norm.eps == 1e-6                      # timm's CLIP variants use nn.LayerNorm defaults

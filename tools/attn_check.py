@@ -60,12 +60,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bwd", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--lib", type=str, default="", help="alternative libxqb200 build (experiments)")
+    ap.add_argument("--skip-check", action="store_true")
     a = ap.parse_args()
+    if a.lib:
+        C.LIB_PATH = os.path.abspath(a.lib)
     dev = torch.device("cuda")
     torch.manual_seed(0)
     shapes = [(2, 128, 2), (1, 16, 1), (2, 1, 1), (2, 129, 3), (3, 200, 2), (2, 513, 4), (2, 514, 2), (1, 769, 2), (2, 499, 3),
               (2, 379, 2), (1, 1024, 1), (1, 333, 12)]
-    for (B, N, H) in shapes:
+    for (B, N, H) in ([] if a.skip_check else shapes):
         for amp in (1.0, 6.0):
             qkv = (torch.randn(B, N, 3 * H * 64, device=dev) * amp).to(torch.bfloat16)
             o_ref, l_ref, _ = ref_attn(qkv, H)
