@@ -105,57 +105,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // warp id among eligible warps, which keeps the single-thread MMA issuer from being starved by the softmax warps
     if (warp >= 4) {
         reg_dec<40>();
-        if (warp == 4 && lane == 0) {
-            // ===== TMA producer =====
-            tma_prefetch_desc(&tmQKV);
+        if (warp == 4) {
+            // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
+            if (elect_one()) tma_prefetch_desc(&tmQKV);
             uint32_t it = 0, tl = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
                 const int bh = t / nQ, qt = t - bh * nQ;
                 const int b = bh / H, h = bh - b * H;
                 const int colQ = h * AT_D, colK = (H + h) * AT_D, colV = (2 * H + h) * AT_D;
                 mbar_wait(q_empty, (tl & 1) ^ 1);
-                mbar_expect_tx(q_full, AT_TILE);
-                tma_load_3d(base + AttnFwdSmem::Q, &tmQKV, colQ, qt * AT_BM, b, q_full);
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, AT_TILE);
+                    tma_load_3d(base + AttnFwdSmem::Q, &tmQKV, colQ, qt * AT_BM, b, q_full);
+                }
+                __syncwarp();
                 for (int j = 0; j < nK; ++j, ++it) {
                     const int st = it % AT_NS;
                     const uint32_t ph = ((it / AT_NS) & 1) ^ 1;
                     mbar_wait(&k_empty[st], ph);
-                    mbar_expect_tx(&k_full[st], AT_TILE);
-                    tma_load_3d(base + AttnFwdSmem::K + st * AT_TILE, &tmQKV, colK, j * AT_BN, b, &k_full[st]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], AT_TILE);
+                        tma_load_3d(base + AttnFwdSmem::K + st * AT_TILE, &tmQKV, colK, j * AT_BN, b, &k_full[st]);
+                    }
+                    __syncwarp();
                     mbar_wait(&v_empty[st], ph);
-                    mbar_expect_tx(&v_full[st], AT_TILE);
-                    tma_load_3d(base + AttnFwdSmem::V + st * AT_TILE, &tmQKV, colV, j * AT_BN, b, &v_full[st]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&v_full[st], AT_TILE);
+                        tma_load_3d(base + AttnFwdSmem::V + st * AT_TILE, &tmQKV, colV, j * AT_BN, b, &v_full[st]);
+                    }
+                    __syncwarp();
                 }
             }
-        } else if (warp == 5 && lane == 0) {
-            // ===== MMA issuer =====
+        } else if (warp == 5) {
+            // ===== MMA issuer (whole warp runs the control flow, one elected lane issues: see elect_one) =====
             const uint64_t qd = desc_k_sw128(smem_u32(base + AttnFwdSmem::Q));
             uint32_t it = 0, tl = 0;
-            auto issue_qk = [&](uint32_t itx, int j) {
+            auto issue_qk = [&](uint32_t itx, int j, bool last_of_tile) {
                 const int st = itx % AT_NS;
                 const int nj = (min(AT_BN, N - j * AT_BN) + 15) & ~15;
                 mbar_wait(&k_full[st], (itx / AT_NS) & 1);
                 tc_fence_after();
-                const uint64_t kd = desc_k_sw128(smem_u32(base + AttnFwdSmem::K + st * AT_TILE));
-                const uint32_t id = idesc_bf16(AT_BM, nj, 0, 0);
+                if (elect_one()) {
+                    const uint64_t kd = desc_k_sw128(smem_u32(base + AttnFwdSmem::K + st * AT_TILE));
+                    const uint32_t id = idesc_bf16(AT_BM, nj, 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(qd, k * 32), desc_adv(kd, k * 32), id, k > 0);
-                umma_commit(&k_empty[st]);
-                umma_commit(s_full);
+                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(qd, k * 32), desc_adv(kd, k * 32), id, k > 0);
+                    umma_commit(&k_empty[st]);
+                    umma_commit(s_full);
+                    if (last_of_tile) umma_commit(q_empty);     // every S MMA of this tile is issued: Q is dead once they retire
+                }
+                __syncwarp();
             };
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
                 mbar_wait(q_full, tl & 1);
                 if (it > 0) { mbar_wait(s_free, (it - 1) & 1); }      // the last S of the previous tile is in registers
                 tc_fence_after();
-                issue_qk(it, 0);
+                issue_qk(it, 0, nK == 1);
                 for (int j = 0; j < nK; ++j, ++it) {
                     if (j + 1 < nK) {
                         mbar_wait(s_free, it & 1);          // softmax holds S_j in registers
                         tc_fence_after();
-                        issue_qk(it + 1, j + 1);
-                        if (j + 2 == nK) umma_commit(q_empty);   // every S MMA of this tile has been issued: Q is dead once they retire
-                    } else if (nK == 1) {
-                        umma_commit(q_empty);
+                        issue_qk(it + 1, j + 1, j + 2 == nK);
                     }
                     const int st = it % AT_NS;
                     const int nj = (min(AT_BN, N - j * AT_BN) + 15) & ~15;
@@ -163,11 +173,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     mbar_wait(p_full, it & 1);              // P_j written (and O rescaled)
                     if (j == 0 && tl > 0) mbar_wait(o_free, (tl - 1) & 1);   // the epilogue has read the previous tile's O
                     tc_fence_after();
-                    const uint64_t vd = desc_mn_sw128(smem_u32(base + AttnFwdSmem::V + st * AT_TILE), 16384, 1024);
-                    const uint32_t id = idesc_bf16(AT_BM, AT_D, 0, 1);
-                    for (int k = 0; k < nj / 16; ++k) umma_ts(tO, tP + k * 8, desc_adv(vd, k * 2048), id, (j | k) != 0);
-                    umma_commit(&v_empty[st]);
-                    umma_commit(pv_done);
+                    if (elect_one()) {
+                        const uint64_t vd = desc_mn_sw128(smem_u32(base + AttnFwdSmem::V + st * AT_TILE), 16384, 1024);
+                        const uint32_t id = idesc_bf16(AT_BM, AT_D, 0, 1);
+                        for (int k = 0; k < nj / 16; ++k) umma_ts(tO, tP + k * 8, desc_adv(vd, k * 2048), id, (j | k) != 0);
+                        umma_commit(&v_empty[st]);
+                        umma_commit(pv_done);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -456,15 +469,17 @@ static bool get_fwd_maps(const void *qkv, void *out, int B, int N, int H, AttnMa
 // =====================================================================================================================
 constexpr int AB_THREADS = 384;
 
+constexpr int AB_QS = 3;            // Q / dO ring stages (a stage is released only when dK_i retires: 2 stages starve the MMAs)
+
 struct AttnBwdSmem {
     static constexpr int K = 0;
     static constexpr int V = AT_TILE;
-    static constexpr int Q = 2 * AT_TILE;           // 2 stages
-    static constexpr int DO = 4 * AT_TILE;          // 2 stages
-    static constexpr int DS = 6 * AT_TILE;          // 2 stages x 2 row tiles
-    static constexpr int DQ = 10 * AT_TILE;         // fp32 staging: 2 row tiles [128][32 fp32]
-    static constexpr int STAT = 12 * AT_TILE;       // lse[2][128], delta[2][128]
-    static constexpr int BAR = STAT + 2048;
+    static constexpr int Q = 2 * AT_TILE;                   // AB_QS stages
+    static constexpr int DO = (2 + AB_QS) * AT_TILE;        // AB_QS stages
+    static constexpr int DS = (2 + 2 * AB_QS) * AT_TILE;    // 2 row tiles (single buffer)
+    static constexpr int DQ = (4 + 2 * AB_QS) * AT_TILE;    // fp32 staging: 2 row tiles [128][32 fp32]
+    static constexpr int STAT = (6 + 2 * AB_QS) * AT_TILE;  // lse[AB_QS][128], delta[AB_QS][128]
+    static constexpr int BAR = STAT + AB_QS * 1024;
     static constexpr int BYTES = BAR + 256;
 };
 
@@ -483,20 +498,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
     uint64_t *kv_full = bars + 0;
-    uint64_t *q_full = bars + 1;      // [2] stages
-    uint64_t *q_empty = bars + 3;     // [2]
-    uint64_t *s_full = bars + 5;      // [2] query halves from here on
-    uint64_t *s_free = bars + 7;
-    uint64_t *dp_full = bars + 9;
-    uint64_t *p_full = bars + 11;
-    uint64_t *dv_done = bars + 13;
-    uint64_t *ds_full = bars + 15;
-    uint64_t *dq_full = bars + 17;
-    uint64_t *dq_free = bars + 18;
-    uint64_t *dkv_done = bars + 19;
-    uint32_t *tmem_holder = (uint32_t *)(bars + 20);
-    float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [2][128]
-    float *s_delta = s_lse + 256;                                // [2][128]
+    uint64_t *q_full = bars + 1;      // [AB_QS] stages
+    uint64_t *q_empty = bars + 4;     // [AB_QS]
+    uint64_t *s_full = bars + 7;      // [2] query halves from here on
+    uint64_t *s_free = bars + 9;
+    uint64_t *dp_full = bars + 11;
+    uint64_t *p_full = bars + 13;
+    uint64_t *dv_done = bars + 15;
+    uint64_t *ds_full = bars + 17;
+    uint64_t *dq_full = bars + 19;
+    uint64_t *dq_free = bars + 20;
+    uint64_t *dkv_done = bars + 21;
+    uint32_t *tmem_holder = (uint32_t *)(bars + 22);
+    float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [AB_QS][128]
+    float *s_delta = s_lse + AB_QS * 128;                        // [AB_QS][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bh = blockIdx.x / nK, jb = blockIdx.x - bh * nK;
@@ -507,8 +522,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
     if (tid == 0) {
         mbar_init(kv_full, 1);
+        for (int i = 0; i < AB_QS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
             mbar_init(&dp_full[i], 1); mbar_init(&p_full[i], 4);
             mbar_init(&dv_done[i], 1); mbar_init(&ds_full[i], 4);
@@ -533,107 +548,123 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // the compute warps it shares a sub-partition with (measured: with the issuer as warp 1 it spent ~130 clk per MMA)
     if (warp >= 8) {
         reg_dec<88>();
-        if (warp == 8 && lane == 0) {
-            // ===== TMA producer =====
-            tma_prefetch_desc(&tmQKV);
-            tma_prefetch_desc(&tmDO);
-            mbar_expect_tx(kv_full, 2 * AT_TILE);
-            tma_load_3d(base + AttnBwdSmem::K, &tmQKV, colK, k0, b, kv_full);
-            tma_load_3d(base + AttnBwdSmem::V, &tmQKV, colV, k0, b, kv_full);
-            for (int i = 0; i < nQ; ++i) {
-                const int st = i & 1;
-                mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&q_full[st], 2 * AT_TILE + 1024);
-                tma_load_3d(base + AttnBwdSmem::Q + st * AT_TILE, &tmQKV, colQ, i * AT_BM, b, &q_full[st]);
-                tma_load_3d(base + AttnBwdSmem::DO + st * AT_TILE, &tmDO, h * AT_D, i * AT_BM, b, &q_full[st]);
-                bulk_load_1d(s_lse + st * 128, lseP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
-                bulk_load_1d(s_delta + st * 128, deltaP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+        if (warp == 8) {
+            // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
+            if (elect_one()) {
+                tma_prefetch_desc(&tmQKV);
+                tma_prefetch_desc(&tmDO);
+                mbar_expect_tx(kv_full, 2 * AT_TILE);
+                tma_load_3d(base + AttnBwdSmem::K, &tmQKV, colK, k0, b, kv_full);
+                tma_load_3d(base + AttnBwdSmem::V, &tmQKV, colV, k0, b, kv_full);
             }
-        } else if (warp == 9 && lane == 0) {
-            // ===== MMA issuer: the two query halves are independent pipelines that share the tensor core =====
-            // descriptors of the four operand tiles, built once (advancing one is a 64-bit add)
+            __syncwarp();
+            for (int i = 0; i < nQ; ++i) {
+                const int st = i % AB_QS;
+                mbar_wait(&q_empty[st], ((i / AB_QS) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&q_full[st], 2 * AT_TILE + 1024);
+                    tma_load_3d(base + AttnBwdSmem::Q + st * AT_TILE, &tmQKV, colQ, i * AT_BM, b, &q_full[st]);
+                    tma_load_3d(base + AttnBwdSmem::DO + st * AT_TILE, &tmDO, h * AT_D, i * AT_BM, b, &q_full[st]);
+                    bulk_load_1d(s_lse + st * 128, lseP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+                    bulk_load_1d(s_delta + st * 128, deltaP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+                }
+                __syncwarp();
+            }
+        } else if (warp == 9) {
+            // ===== MMA issuer (whole warp runs the control flow, one elected lane issues: see elect_one).  S^T and dP^T are
+            // issued full width (N = the block's queries; a 64-wide SS MMA is shared-memory-bound at 48 clk, a 128-wide one
+            // runs at the 64 clk tensor rate), then signalled per half; dV / dK / dQ follow each half's P / dS.
             const uint64_t kd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::K)), vd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::V));
             const uint64_t kd_mn = desc_mn_sw128(smem_u32(base + AttnBwdSmem::K), 16384, 1024);
             const uint64_t qd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::Q)), dd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::DO));
             const uint64_t qd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::Q), 16384, 1024);
             const uint64_t dd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DO), 16384, 1024);
-            const uint64_t dsd0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
-            auto issue_s = [&](int i, int hf) {
-                const int n = nq_half(i, hf);
-                if (n == 0) return;
-                const uint64_t qd = desc_adv(qd_k0, (i & 1) * AT_TILE + hf * 8192);
-                const uint32_t id = idesc_bf16(AT_BN, n, 0, 0);
+            const uint64_t dsd = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
+            auto nq_all = [&](int i) { return (min(AT_BM, N - i * AT_BM) + 15) & ~15; };
+            auto issue_s = [&](int i) {          // caller: both halves' S are in registers (s_free) and Q_i has landed
+                if (elect_one()) {
+                    const uint64_t qd = desc_adv(qd_k0, (i % AB_QS) * AT_TILE);
+                    const uint32_t id = idesc_bf16(AT_BN, nq_all(i), 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS + hf * 64, desc_adv(kd_k, k * 32), desc_adv(qd, k * 32), id, k > 0);
-                umma_commit(&s_full[hf]);
+                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(kd_k, k * 32), desc_adv(qd, k * 32), id, k > 0);
+                    umma_commit(&s_full[0]);
+                    if (nq_half(i, 1) > 0) umma_commit(&s_full[1]);
+                }
+                __syncwarp();
             };
-            auto issue_dp = [&](int i, int hf) {
-                const int n = nq_half(i, hf);
-                if (n == 0) return;
-                const uint64_t dd = desc_adv(dd_k0, (i & 1) * AT_TILE + hf * 8192);
-                const uint32_t id = idesc_bf16(AT_BN, n, 0, 0);
+            auto issue_dp = [&](int i) {
+                if (elect_one()) {
+                    const uint64_t dd = desc_adv(dd_k0, (i % AB_QS) * AT_TILE);
+                    const uint32_t id = idesc_bf16(AT_BN, nq_all(i), 0, 0);
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP + hf * 64, desc_adv(vd_k, k * 32), desc_adv(dd, k * 32), id, k > 0);
-                umma_commit(&dp_full[hf]);
+                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_adv(vd_k, k * 32), desc_adv(dd, k * 32), id, k > 0);
+                    umma_commit(&dp_full[0]);
+                    if (nq_half(i, 1) > 0) umma_commit(&dp_full[1]);
+                }
+                __syncwarp();
             };
             const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
             const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
-            bool dv_started = false, dk_started = false;
-            // per-half completion counters of the barriers this thread waits on (a half with no queries is skipped on both sides)
+            uint32_t dv_started = 0, dk_started = 0;
+            // per-half completion counters of the barriers this warp waits on (a half with no queries is skipped on both sides)
             uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0}, n_dsfull[2] = {0, 0};
             mbar_wait(kv_full, 0);
             mbar_wait(&q_full[0], 0);
             tc_fence_after();
-            issue_s(0, 0);
-            issue_s(0, 1);
-            issue_dp(0, 0);
-            issue_dp(0, 1);
+            issue_s(0);
+            issue_dp(0);
             for (int i = 0; i < nQ; ++i) {
-                const int st = i & 1;
+                const int st = i % AB_QS;
                 const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
                 const bool more = i + 1 < nQ;
-                if (more) { mbar_wait(&q_full[st ^ 1], ((i + 1) >> 1) & 1); }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const int ks = nq_half(i, hf) / 16;
                     if (ks > 0) {
                         mbar_wait(&p_full[hf], n_pfull[hf]++ & 1);
-                        XQ_TR(i < 30, 16 * i + hf);
+                        XQ_TR(i < 30 && lane == 0, 16 * i + hf);
                         tc_fence_after();
-                        for (int k = 0; k < ks; ++k) {    // dV += P^T dO : query k-step k of this half
-                            umma_ts(tDV, tP + hf * 32 + k * 8, desc_adv(dd_mn, hf * 8192 + k * 2048), id_acc, dv_started ? 1u : 0u);
-                            dv_started = true;
+                        if (elect_one()) {
+                            for (int k = 0; k < ks; ++k)      // dV += P^T dO : query k-step k of this half
+                                umma_ts(tDV, tP + hf * 32 + k * 8, desc_adv(dd_mn, hf * 8192 + k * 2048), id_acc, dv_started | (uint32_t)k);
+                            umma_commit(&dv_done[hf]);
                         }
-                        umma_commit(&dv_done[hf]);
+                        __syncwarp();
+                        dv_started = 1;
                         mbar_wait(&s_free[hf], n_sfree[hf]++ & 1);      // (arrived before p_full) S of this half is in registers
-                        tc_fence_after();
                     }
-                    if (more) issue_s(i + 1, hf);
+                }
+                if (more) {
+                    mbar_wait(&q_full[(i + 1) % AB_QS], ((i + 1) / AB_QS) & 1);
+                    tc_fence_after();
+                    issue_s(i + 1);
                 }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     const int ks = nq_half(i, hf) / 16;
                     mbar_wait(&ds_full[hf], n_dsfull[hf]++ & 1);        // always arrives (an empty half still zero-fills its dS tile)
-                    XQ_TR(i < 30, 16 * i + 2 + hf);
+                    XQ_TR(i < 30 && lane == 0, 16 * i + 2 + hf);
                     tc_fence_after();
-                    for (int k = 0; k < ks; ++k) {        // dK += dS^T Q : dS^T (bf16) sits over this half's dP^T columns
-                        umma_ts(tDK, tDP + hf * 64 + k * 8, desc_adv(qd_mn, hf * 8192 + k * 2048), id_acc, dk_started ? 1u : 0u);
-                        dk_started = true;
-                    }
-                    if (hf == 1) {
-                        umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
-                        if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
-                        const uint64_t dsd = desc_adv(dsd0, st * 2 * AT_TILE);
+                    if (hf == 1 && i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
+                    if (elect_one()) {
+                        for (int k = 0; k < ks; ++k)          // dK += dS^T Q : dS^T (bf16) sits over this half's dP^T columns
+                            umma_ts(tDK, tDP + hf * 64 + k * 8, desc_adv(qd_mn, hf * 8192 + k * 2048), id_acc, dk_started | (uint32_t)k);
+                        if (hf == 1) {
+                            umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
 #pragma unroll
-                        for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
-                            umma_ss(tDQ, desc_adv(dsd, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
-                        umma_commit(dq_full);
-                        XQ_TR(i < 30, 16 * i + 4);
+                            for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
+                                umma_ss(tDQ, desc_adv(dsd, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
+                            umma_commit(dq_full);
+                        }
                     }
-                    if (more) issue_dp(i + 1, hf);
+                    __syncwarp();
+                    if (ks > 0) dk_started = 1;
+                    if (hf == 1) XQ_TR(i < 30 && lane == 0, 16 * i + 4);
                 }
+                if (more) issue_dp(i + 1);
             }
-            umma_commit(dkv_done);
+            if (elect_one()) umma_commit(dkv_done);
+            __syncwarp();
         }
     } else {
         reg_inc<208>();
@@ -672,10 +703,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
         };
         for (int i = 0; i < nQ; ++i) {
-            const int st = i & 1;
+            const int st = i % AB_QS;
             const int ncol = nq_half(i, hf);                        // columns of this half the MMAs produce
-            mbar_wait(&q_full[st], (i >> 1) & 1);                   // statistics of this query block are in smem
-            const uint32_t dsrow = smem_u32(base + AttnBwdSmem::DS + st * 2 * AT_TILE + hf * AT_TILE);
+            mbar_wait(&q_full[st], (i / AB_QS) & 1);                // statistics of this query block are in smem
+            // single dS buffer: dS_i is written after drain_dq(i - 1), i.e. after the dQ_{i-1} MMA that read it completed
+            const uint32_t dsrow = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
             if (ncol == 0) {
                 // no query of this block falls in this half: its dS tile must still read as zero for the dQ MMA
                 if (i > 0) drain_dq(i - 1);
@@ -782,7 +814,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         {
             const uint32_t src = hf == 0 ? tDV : tDK;
             const float mul = hf == 0 ? 1.0f : scale;
-            uint8_t *so = base + AttnBwdSmem::Q + hf * AT_TILE;      // both Q stages are dead
+            uint8_t *so = base + AttnBwdSmem::Q + hf * AT_TILE;      // every Q stage is dead
             const uint32_t so_a = smem_u32(so);
 #pragma unroll
             for (int c0 = 0; c0 < AT_D; c0 += 16) {

@@ -185,6 +185,16 @@ __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
 // advance a shared-memory matrix descriptor by `bytes` (start-address field is in 16-byte units; never carries out of it)
 __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
+// one lane of a CONVERGED warp.  The single-thread tcgen05 / TMA instructions take uniform-register operands: issued
+// under `if (lane == 0)` (a divergent region) the compiler wraps each one in an ELECT / BRA.U.ANY serialisation loop,
+// measured at ~112 clk per tcgen05.mma whatever its shape; issued under elect.sync by a warp that runs the surrounding
+// control flow uniformly they are plain predicated instructions (64 clk for M128 N128 K16 = the tensor-pipe rate).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- misc ------------------------------------------------------------------------------------------------
 // byte offset of element (row r, column c) of a [rows][64 bf16] SWIZZLE_128B row tile
 __host__ __device__ __forceinline__ uint32_t rowtile_off_bf16(int r, int c) {

@@ -151,6 +151,88 @@ tma_probe_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     __syncthreads();
 }
 
+// timing: `reps` back-to-back MMAs of one flavour (same operands, accumulating), one commit; clocks measured by the issuer
+//   flavour 0: SS K x K, N = n   1: TS (A tmem) x B MN-major, N = 64   2: SS A MN x B MN, N = 64   3: SS K x K with B = 64-row half tile
+__global__ void __launch_bounds__(128, 1) mma_time_kernel(int flavour, int n, int reps, long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base, *sB = base + 32768;
+    uint64_t *bar = (uint64_t *)(base + 49152);
+    uint32_t *tptr = (uint32_t *)(base + 49152 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tptr);
+    for (int i = tid; i < 49152 / 4; i += 128) ((uint32_t *)base)[i] = 0x3c003c00u;   // finite bf16 values
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tptr;
+    if (tid == 0) {
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const int k = r & 3;
+            if (flavour == 0) umma_ss(tmem, desc_k_sw128(smem_u32(sA) + k * 32), desc_k_sw128(smem_u32(sB) + k * 32), idesc_bf16(128, n, 0, 0), 1);
+            else if (flavour == 1) umma_ts(tmem, tmem + 256 + k * 8, desc_mn_sw128(smem_u32(sB) + k * 2048, 16384, 1024), idesc_bf16(128, 64, 0, 1), 1);
+            else if (flavour == 2) umma_ss(tmem, desc_mn_sw128(smem_u32(sA) + k * 2048, 16384, 1024), desc_mn_sw128(smem_u32(sB) + k * 2048, 16384, 1024), idesc_bf16(128, 64, 1, 1), 1);
+            else umma_ss(tmem, desc_k_sw128(smem_u32(sA) + k * 32), desc_mn_sw128(smem_u32(sB) + k * 2048, 16384, 1024), idesc_bf16(128, n, 0, 1), 1);
+        }
+        long long t1 = clock64();
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+// same measurement, but the WHOLE warp runs the loop and only the MMA is predicated by elect.sync (CUTLASS style)
+__global__ void __launch_bounds__(128, 1) mma_time_kernel_elect(int n, int reps, long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base, *sB = base + 32768;
+    uint64_t *bar = (uint64_t *)(base + 49152);
+    uint32_t *tptr = (uint32_t *)(base + 49152 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(tptr);
+    for (int i = tid; i < 49152 / 4; i += 128) ((uint32_t *)base)[i] = 0x3c003c00u;
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tptr;
+    if (warp == 1) {
+        const uint64_t ad = desc_k_sw128(smem_u32(sA)), bd = desc_k_sw128(smem_u32(sB));
+        const uint32_t id = idesc_bf16(128, n, 0, 0);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; r += 4) {
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_ss(tmem, ad + 2 * k, bd + 2 * k, id, 1);
+            }
+            __syncwarp();
+        }
+        long long t1 = clock64();
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+        mbar_wait(bar, 0);
+        long long t2 = clock64();
+        if (tid == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 static float bf(bf16 x) { return __bfloat162float(x); }
 
 int main() {
@@ -285,6 +367,35 @@ int main() {
                 }
         printf("T3d TMA 3-D store (row clipping at N): mismatches = %d  %s\n", bad, bad == 0 ? "PASS" : "FAIL");
         fails += bad != 0;
+    }
+    {
+        long long *dout, hout[2];
+        CK(cudaMalloc(&dout, 16));
+        CK(cudaFuncSetAttribute(mma_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        struct { int fl, n; const char *name; } cases[] = {
+            {0, 128, "SS  A K-major x B K-major   M128 N128 K16"}, {0, 64, "SS  A K-major x B K-major   M128 N64  K16"},
+            {0, 16, "SS  A K-major x B K-major   M128 N16  K16"}, {1, 64, "TS  A tmem    x B MN-major  M128 N64  K16"},
+            {2, 64, "SS  A MN-major x B MN-major M128 N64  K16"}, {3, 64, "SS  A K-major x B MN-major  M128 N64  K16"}};
+        for (auto &c : cases)
+            for (int reps : {64, 256}) {
+                mma_time_kernel<<<1, 128, SMEM>>>(c.fl, c.n, reps, dout);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(hout, dout, 16, cudaMemcpyDeviceToHost));
+                printf("T4 %-58s reps %3d: issue %6.1f clk/MMA, issue+drain %6.1f clk/MMA\n", c.name, reps, (double)hout[0] / reps, (double)hout[1] / reps);
+            }
+    }
+    {
+        long long *dout, hout[2];
+        CK(cudaMalloc(&dout, 16));
+        CK(cudaFuncSetAttribute(mma_time_kernel_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        for (int n : {128, 64, 16})
+            for (int reps : {64, 256}) {
+                mma_time_kernel_elect<<<1, 128, SMEM>>>(n, reps, dout);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(hout, dout, 16, cudaMemcpyDeviceToHost));
+                printf("T5 elect.sync issue, SS K x K M128 N%-3d reps %3d: issue %6.1f clk/MMA, issue+drain %6.1f clk/MMA\n", n, reps,
+                       (double)hout[0] / reps, (double)hout[1] / reps);
+            }
     }
     printf("umma_probe: %s (%d failing checks)\n", fails ? "FAILED" : "ALL PASS", fails);
     return 0;
