@@ -337,7 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // The last (N mod 128) query rows when they are few (AT_TAIL_MAX): one warp per (batch*head, row) on the CUDA cores --
 // a 1-row tile would cost a full 128-row MMA tile in attn_fwd_kernel (S = 513: 20 % of its work).  Lanes split the keys,
 // each with its own online softmax, merged by shuffles at the end.  Same outputs as the tile kernel (out row, lse2).
-constexpr int AT_TAIL_MAX = 1;
+constexpr int AT_TAIL_MAX = 0;     // 0: ragged query tiles always run on the tile kernel (dead warps skip the softmax math)
 
 __global__ void __launch_bounds__(128)
 attn_fwd_tail_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out, float *__restrict__ lse2, int B, int N,
@@ -462,12 +462,17 @@ static bool get_fwd_maps(const void *qkv, void *out, int B, int N, int H, AttnMa
 // The query tail is cheap (it is the MMA N / K extent, rounded to 16); `scale` is folded into the dK epilogue and the
 // dQ conversion.  dQ is accumulated across the key blocks of a (batch, head) in an fp32 workspace by TMA reduce-add
 // and converted to bf16 into dqkv by attn_dq_convert_kernel.
-// Warps: 0-7 = compute (warp % 4 = TMEM lane quarter, warp / 4 = query half), 8 = TMA producer, 9 = MMA issuer.
-// The two query halves (64 queries each) are INDEPENDENT pipelines -- own S / dP / P columns, own barriers, own MMAs
-// (N = 64), own dQ drain -- that only share the tensor core and the dQ MMA: while one warpgroup is in its exp2 (MUFU)
-// phase the other is in its dS (FMA) phase, which is what keeps both pipes busy with a single CTA per SM.
+// Warp-specialised, 24 warps (warp % 4 = TMEM lane quarter; "half" = 64 of the block's 128 queries):
+//   wgE  warps 0-7    P^T = exp2(...)                  one warpgroup per query half   (the MUFU work)
+//   wgD  warps 8-15   dS^T = P^T o (dP^T - delta)      one warpgroup per query half, written to TMEM (dK operand) and
+//                                                      smem (dQ operand)              (the FMA work)
+//   ctl  warps 16-19  16 = TMA producer, 17 = MMA issuer
+//   wgQ  warps 20-23  drains each dQ_i partial: TMEM -> fp32 smem -> TMA reduce-add
+// The exp2 of block i+1 (MUFU pipe) overlaps the dS arithmetic of block i (FMA pipe), the dQ drain never sits on either's
+// critical path, and every sub-partition holds two warps of each elementwise role (latency hiding).  wgD reads P^T back
+// from TMEM as bf16 (the same rounded values the dV MMA consumes).
 // =====================================================================================================================
-constexpr int AB_THREADS = 384;
+constexpr int AB_THREADS = 768;
 
 constexpr int AB_QS = 3;            // Q / dO ring stages (a stage is released only when dK_i retires: 2 stages starve the MMAs)
 
@@ -476,9 +481,9 @@ struct AttnBwdSmem {
     static constexpr int V = AT_TILE;
     static constexpr int Q = 2 * AT_TILE;                   // AB_QS stages
     static constexpr int DO = (2 + AB_QS) * AT_TILE;        // AB_QS stages
-    static constexpr int DS = (2 + 2 * AB_QS) * AT_TILE;    // 2 row tiles (single buffer)
-    static constexpr int DQ = (4 + 2 * AB_QS) * AT_TILE;    // fp32 staging: 2 row tiles [128][32 fp32]
-    static constexpr int STAT = (6 + 2 * AB_QS) * AT_TILE;  // lse[AB_QS][128], delta[AB_QS][128]
+    static constexpr int DS = (2 + 2 * AB_QS) * AT_TILE;    // 2 buffers x 2 row tiles
+    static constexpr int DQ = (6 + 2 * AB_QS) * AT_TILE;    // fp32 staging: ONE row tile [128][32 fp32] (two passes per dQ_i)
+    static constexpr int STAT = (7 + 2 * AB_QS) * AT_TILE;  // lse[AB_QS][128], delta[AB_QS][128]
     static constexpr int BAR = STAT + AB_QS * 1024;
     static constexpr int BYTES = BAR + 256;
 };
@@ -500,16 +505,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint64_t *kv_full = bars + 0;
     uint64_t *q_full = bars + 1;      // [AB_QS] stages
     uint64_t *q_empty = bars + 4;     // [AB_QS]
-    uint64_t *s_full = bars + 7;      // [2] query halves from here on
-    uint64_t *s_free = bars + 9;
-    uint64_t *dp_full = bars + 11;
-    uint64_t *p_full = bars + 13;
-    uint64_t *dv_done = bars + 15;
-    uint64_t *ds_full = bars + 17;
-    uint64_t *dq_full = bars + 19;
-    uint64_t *dq_free = bars + 20;
-    uint64_t *dkv_done = bars + 21;
-    uint32_t *tmem_holder = (uint32_t *)(bars + 22);
+    uint64_t *s_full = bars + 7;      // S^T_i in TMEM                      (MMA commit)
+    uint64_t *s_free = bars + 8;      // S^T_i in wgE's registers           (4 warps)
+    uint64_t *p_full = bars + 9;      // P^T_i (bf16) in TMEM               (4 warps of wgE)
+    uint64_t *p_read = bars + 10;     // P^T_i in wgD's registers           (4 warps of wgD)
+    uint64_t *dv_done = bars + 11;    // dV MMAs of block i retired         (MMA commit)
+    uint64_t *dp_full = bars + 12;    // dP^T_i in TMEM                     (MMA commit)
+    uint64_t *ds_full = bars + 13;    // dS_i in TMEM and smem              (4 warps of wgD)
+    uint64_t *dq_full = bars + 14;    // dQ_i partial in TMEM               (MMA commit)
+    uint64_t *dq_free = bars + 15;    // dQ_i drained                       (4 warps of wgQ)
+    uint64_t *dkv_done = bars + 16;
+    uint32_t *tmem_holder = (uint32_t *)(bars + 17);
     float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [AB_QS][128]
     float *s_delta = s_lse + AB_QS * 128;                        // [AB_QS][128]
 
@@ -523,32 +529,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (tid == 0) {
         mbar_init(kv_full, 1);
         for (int i = 0; i < AB_QS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
-            mbar_init(&dp_full[i], 1); mbar_init(&p_full[i], 4);
-            mbar_init(&dv_done[i], 1); mbar_init(&ds_full[i], 4);
-        }
-        mbar_init(dq_full, 1);
-        mbar_init(dq_free, 8);
-        mbar_init(dkv_done, 1);
+        mbar_init(s_full, 1); mbar_init(s_free, 8);
+        mbar_init(p_full, 8); mbar_init(p_read, 8);
+        mbar_init(dv_done, 1); mbar_init(dp_full, 1);
+        mbar_init(ds_full, 8); mbar_init(dq_full, 1);
+        mbar_init(dq_free, 4); mbar_init(dkv_done, 1);
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc<512>(tmem_holder);
+    if (warp == 17) tmem_alloc<512>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
     const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tP = tmem + 448;
     XQ_TR(tid == 0, 16 * 30 + 2);
-    // queries of block i that half hf holds, rounded up to the MMA granularity (0 when the block ends before the half)
-    auto nq_half = [&](int i, int hf) { return max(0, min(64, ((min(AT_BM, N - i * AT_BM) + 15) & ~15) - hf * 64)); };
+    // queries of block i, rounded up to the MMA granularity
+    auto nq_of = [&](int i) { return (min(AT_BM, N - i * AT_BM) + 15) & ~15; };
+    const int qd = warp & 3;                         // TMEM lane quarter of this warp
+    const int krow = qd * 32 + lane;                 // row of the 128-row tile this thread owns (a key, or a query in wgQ)
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
 
-    // warps 0-3 / 4-7 = compute warpgroups (query halves 0 / 1), warps 8-11 = control (8 = TMA producer, 9 = MMA issuer):
-    // the scheduler favours the higher warp id among eligible warps, so the single-thread MMA issuer is never starved by
-    // the compute warps it shares a sub-partition with (measured: with the issuer as warp 1 it spent ~130 clk per MMA)
-    if (warp >= 8) {
-        reg_dec<88>();
-        if (warp == 8) {
+    // register budget (768 threads x 80 at launch = 61440): 4 compute warpgroups x 88 + control 72 + wgQ 56 = 6 x 80
+    if (warp >= 16 && warp < 20) {
+        reg_dec<72>();
+        if (warp == 16) {
             // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
             if (elect_one()) {
                 tma_prefetch_desc(&tmQKV);
@@ -570,44 +574,39 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 __syncwarp();
             }
-        } else if (warp == 9) {
-            // ===== MMA issuer (whole warp runs the control flow, one elected lane issues: see elect_one).  S^T and dP^T are
-            // issued full width (N = the block's queries; a 64-wide SS MMA is shared-memory-bound at 48 clk, a 128-wide one
-            // runs at the 64 clk tensor rate), then signalled per half; dV / dK / dQ follow each half's P / dS.
+        } else if (warp == 17) {
+            // ===== MMA issuer (whole warp runs the control flow, one elected lane issues: see elect_one) =====
+            // program order per query block i:   S^T_{i+1}  |  dV += P^T_i dO_i  |  dK += dS^T_i Q_i ; dP^T_{i+1} ; dQ_i = dS_i K
+            // (S^T_{i+1} only needs S^T_i to have left TMEM, so wgE never waits for it; dP^T_{i+1} is queued right behind
+            //  dK_i -- which reads dS^T_i out of the same columns -- so wgD gets it back after two MMA groups)
             const uint64_t kd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::K)), vd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::V));
             const uint64_t kd_mn = desc_mn_sw128(smem_u32(base + AttnBwdSmem::K), 16384, 1024);
             const uint64_t qd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::Q)), dd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::DO));
             const uint64_t qd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::Q), 16384, 1024);
             const uint64_t dd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DO), 16384, 1024);
             const uint64_t dsd = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
-            auto nq_all = [&](int i) { return (min(AT_BM, N - i * AT_BM) + 15) & ~15; };
-            auto issue_s = [&](int i) {          // caller: both halves' S are in registers (s_free) and Q_i has landed
+            const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
+            const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
+            auto issue_s = [&](int i) {
                 if (elect_one()) {
-                    const uint64_t qd = desc_adv(qd_k0, (i % AB_QS) * AT_TILE);
-                    const uint32_t id = idesc_bf16(AT_BN, nq_all(i), 0, 0);
+                    const uint64_t qdk = desc_adv(qd_k0, (i % AB_QS) * AT_TILE);
+                    const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
-                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(kd_k, k * 32), desc_adv(qd, k * 32), id, k > 0);
-                    umma_commit(&s_full[0]);
-                    if (nq_half(i, 1) > 0) umma_commit(&s_full[1]);
+                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(kd_k, k * 32), desc_adv(qdk, k * 32), id, k > 0);
+                    umma_commit(s_full);
                 }
                 __syncwarp();
             };
             auto issue_dp = [&](int i) {
                 if (elect_one()) {
-                    const uint64_t dd = desc_adv(dd_k0, (i % AB_QS) * AT_TILE);
-                    const uint32_t id = idesc_bf16(AT_BN, nq_all(i), 0, 0);
+                    const uint64_t ddk = desc_adv(dd_k0, (i % AB_QS) * AT_TILE);
+                    const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
-                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_adv(vd_k, k * 32), desc_adv(dd, k * 32), id, k > 0);
-                    umma_commit(&dp_full[0]);
-                    if (nq_half(i, 1) > 0) umma_commit(&dp_full[1]);
+                    for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_adv(vd_k, k * 32), desc_adv(ddk, k * 32), id, k > 0);
+                    umma_commit(dp_full);
                 }
                 __syncwarp();
             };
-            const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
-            const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
-            uint32_t dv_started = 0, dk_started = 0;
-            // per-half completion counters of the barriers this warp waits on (a half with no queries is skipped on both sides)
-            uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0}, n_dsfull[2] = {0, 0};
             mbar_wait(kv_full, 0);
             mbar_wait(&q_full[0], 0);
             tc_fence_after();
@@ -615,237 +614,273 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             issue_dp(0);
             for (int i = 0; i < nQ; ++i) {
                 const int st = i % AB_QS;
+                const int ks = nq_of(i) / 16;
                 const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
                 const bool more = i + 1 < nQ;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int ks = nq_half(i, hf) / 16;
-                    if (ks > 0) {
-                        mbar_wait(&p_full[hf], n_pfull[hf]++ & 1);
-                        XQ_TR(i < 30 && lane == 0, 16 * i + hf);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            for (int k = 0; k < ks; ++k)      // dV += P^T dO : query k-step k of this half
-                                umma_ts(tDV, tP + hf * 32 + k * 8, desc_adv(dd_mn, hf * 8192 + k * 2048), id_acc, dv_started | (uint32_t)k);
-                            umma_commit(&dv_done[hf]);
-                        }
-                        __syncwarp();
-                        dv_started = 1;
-                        mbar_wait(&s_free[hf], n_sfree[hf]++ & 1);      // (arrived before p_full) S of this half is in registers
-                    }
-                }
                 if (more) {
+                    mbar_wait(s_free, i & 1);
                     mbar_wait(&q_full[(i + 1) % AB_QS], ((i + 1) / AB_QS) & 1);
                     tc_fence_after();
                     issue_s(i + 1);
                 }
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    const int ks = nq_half(i, hf) / 16;
-                    mbar_wait(&ds_full[hf], n_dsfull[hf]++ & 1);        // always arrives (an empty half still zero-fills its dS tile)
-                    XQ_TR(i < 30 && lane == 0, 16 * i + 2 + hf);
-                    tc_fence_after();
-                    if (hf == 1 && i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
-                    if (elect_one()) {
-                        for (int k = 0; k < ks; ++k)          // dK += dS^T Q : dS^T (bf16) sits over this half's dP^T columns
-                            umma_ts(tDK, tDP + hf * 64 + k * 8, desc_adv(qd_mn, hf * 8192 + k * 2048), id_acc, dk_started | (uint32_t)k);
-                        if (hf == 1) {
-                            umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
-#pragma unroll
-                            for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
-                                umma_ss(tDQ, desc_adv(dsd, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
-                            umma_commit(dq_full);
-                        }
-                    }
-                    __syncwarp();
-                    if (ks > 0) dk_started = 1;
-                    if (hf == 1) XQ_TR(i < 30 && lane == 0, 16 * i + 4);
+                mbar_wait(p_full, i & 1);
+                XQ_TR(i < 30 && lane == 0, 16 * i + 0);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int k = 0; k < ks; ++k)      // dV += P^T dO : 16 queries per k-step
+                        umma_ts(tDV, tP + k * 8, desc_adv(dd_mn, k * 2048), id_acc, (uint32_t)(i | k));   // P^T: 8 columns per k-step, contiguous
+                    umma_commit(dv_done);
                 }
+                __syncwarp();
+                mbar_wait(ds_full, i & 1);
+                XQ_TR(i < 30 && lane == 0, 16 * i + 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int k = 0; k < ks; ++k)      // dK += dS^T Q : each query half keeps its dS^T (bf16) over the start of its own dP^T columns
+                        umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_adv(qd_mn, k * 2048), id_acc, (uint32_t)(i | k));
+                    umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
+                }
+                __syncwarp();
                 if (more) issue_dp(i + 1);
+                if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
+                if (elect_one()) {
+                    const uint64_t dsi = desc_adv(dsd, (i & 1) * 2 * AT_TILE);
+#pragma unroll
+                    for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
+                        umma_ss(tDQ, desc_adv(dsi, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
+                    umma_commit(dq_full);
+                }
+                __syncwarp();
+                XQ_TR(i < 30 && lane == 0, 16 * i + 2);
             }
             if (elect_one()) umma_commit(dkv_done);
             __syncwarp();
         }
-    } else {
-        reg_inc<208>();
-        // ===== compute: thread = (key lane, query half); the two halves run as independent warpgroups =====
-        const int qd = warp & 3;                     // TMEM lane quarter
-        const int hf = warp >> 2;                    // query half: columns [hf*64, hf*64+64)
-        const int krow = qd * 32 + lane;             // key row inside the block
+    } else if (warp < 8) {
+        reg_inc<88>();
+        // ===== wgE (warps 0-7): P^T = exp2(S^T c - L2[q]); thread = (key row, query half hf): the MUFU warpgroups =====
+        const int hf = warp >> 2;
         const bool key_ok = k0 + krow < N;
         const bool keys_full = k0 + AT_BN <= N;      // warp-uniform: no key of this block needs masking
-        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-        const int wtid = tid & 127;                  // thread index inside the warpgroup
-        uint32_t n_sfull = 0, n_dpfull = 0, n_dvdone = 0;
-        auto drain_dq = [&](int i) {
-            // this warpgroup's 32 head-dim columns of dQ_i (TMEM lanes = queries) -> fp32 smem row tile -> TMA reduce-add
-            mbar_wait(dq_full, i & 1);
-            tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(tDQ + lane_addr + hf * 32, r);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_free);
-            if (wtid == 0) bulk_wait_read<0>();      // this warpgroup's previous reduce has finished reading its staging tile
-            named_bar_sync(2 + hf, 128);
-            uint8_t *dst = base + AttnBwdSmem::DQ + hf * AT_TILE;
-            const uint32_t dst_a = smem_u32(dst);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) sts128(dst_a + rowtile_unit(krow, u), make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]));
-            fence_async_smem();
-            named_bar_sync(4 + hf, 128);
-            if (wtid == 0) {
-#ifndef XQ_ATTN_EXP_NODQ      // experiment switch (tools/): time the kernel without the dQ reduce traffic
-                tma_reduce_add_3d(&tmDQ, dst, hf * 32, i * AT_BM, bh);
-#endif
-                bulk_commit();
-            }
-        };
         for (int i = 0; i < nQ; ++i) {
             const int st = i % AB_QS;
-            const int ncol = nq_half(i, hf);                        // columns of this half the MMAs produce
+            const int nqr = nq_of(i);
             mbar_wait(&q_full[st], (i / AB_QS) & 1);                // statistics of this query block are in smem
-            // single dS buffer: dS_i is written after drain_dq(i - 1), i.e. after the dQ_{i-1} MMA that read it completed
-            const uint32_t dsrow = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
-            if (ncol == 0) {
-                // no query of this block falls in this half: its dS tile must still read as zero for the dQ MMA
-                if (i > 0) drain_dq(i - 1);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) sts128(dsrow + rowtile_unit(krow, u), make_uint4(0u, 0u, 0u, 0u));
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ds_full[hf]);
-                continue;
-            }
-            mbar_wait(&s_full[hf], n_sfull++ & 1);
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 6 + 5 * hf);
+            mbar_wait(s_full, i & 1);
+            XQ_TR(i < 30 && warp == 0 && lane == 0, 16 * i + 4);
             tc_fence_after();
-            float p[64];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-                if (ch * 16 < ncol) tmem_ld16(tS + lane_addr + hf * 64 + ch * 16, *reinterpret_cast<uint32_t(*)[16]>(&p[ch * 16]));
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[hf]);
             const uint32_t l4 = smem_u32(s_lse + st * 128 + hf * 64);
-            if (keys_full && ncol == 64) {
+            const bool fast = keys_full && nqr == AT_BM;
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    const float4 L = lds128f(l4 + g * 16);
-                    p[4 * g + 0] = ex2_approx(fmaf(p[4 * g + 0], c, -L.x));
-                    p[4 * g + 1] = ex2_approx(fmaf(p[4 * g + 1], c, -L.y));
-                    p[4 * g + 2] = ex2_approx(fmaf(p[4 * g + 2], c, -L.z));
-                    p[4 * g + 3] = ex2_approx(fmaf(p[4 * g + 3], c, -L.w));
+            for (int ch = 0; ch < 2; ++ch) {                        // 2 chunks of 32 queries
+                const int col = hf * 64 + ch * 32;
+                uint32_t sb[32];
+                if (col < nqr) tmem_ld32(tS + lane_addr + col, sb);
+                tmem_wait_ld();
+                if (ch == 1) {                                      // this half of S^T_i has left TMEM
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
                 }
-            } else {
-#pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    const float4 L = lds128f(l4 + g * 16);
-                    const bool ok = key_ok && ((g >> 2) * 16 < ncol);
-                    p[4 * g + 0] = ok ? ex2_approx(fmaf(p[4 * g + 0], c, -L.x)) : 0.f;
-                    p[4 * g + 1] = ok ? ex2_approx(fmaf(p[4 * g + 1], c, -L.y)) : 0.f;
-                    p[4 * g + 2] = ok ? ex2_approx(fmaf(p[4 * g + 2], c, -L.z)) : 0.f;
-                    p[4 * g + 3] = ok ? ex2_approx(fmaf(p[4 * g + 3], c, -L.w)) : 0.f;
-                }
-            }
-            if (n_dvdone < n_sfull - 1) { mbar_wait(&dv_done[hf], n_dvdone++ & 1); tc_fence_after(); }   // the P buffer of this half is free
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[ch * 32 + 2 * e], p[ch * 32 + 2 * e + 1]);
+                for (int g = 0; g < 8; ++g) {
+                    const float4 L = lds128f(l4 + (ch * 8 + g) * 16);
+                    float p0 = ex2_approx(fmaf(__uint_as_float(sb[4 * g + 0]), c, -L.x));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(sb[4 * g + 1]), c, -L.y));
+                    float p2 = ex2_approx(fmaf(__uint_as_float(sb[4 * g + 2]), c, -L.z));
+                    float p3 = ex2_approx(fmaf(__uint_as_float(sb[4 * g + 3]), c, -L.w));
+                    if (!fast) {
+                        const bool ok = key_ok && (col < nqr);
+                        p0 = ok ? p0 : 0.f; p1 = ok ? p1 : 0.f; p2 = ok ? p2 : 0.f; p3 = ok ? p3 : 0.f;
+                    }
+                    pk[2 * g] = pack_bf16(p0, p1);
+                    pk[2 * g + 1] = pack_bf16(p2, p3);
+                }
+                if (ch == 0 && i > 0) {                             // the P buffer is free: dV_{i-1} retired and wgD holds P_{i-1}
+                    mbar_wait(dv_done, (i - 1) & 1);
+                    mbar_wait(p_read, (i - 1) & 1);
+                    tc_fence_after();
+                }
                 tmem_st16(tP + lane_addr + hf * 32 + ch * 16, pk);
             }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[hf]);
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 7 + 5 * hf);
-            if (i > 0) drain_dq(i - 1);
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 8 + 5 * hf);
-            mbar_wait(&dp_full[hf], n_dpfull++ & 1);
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 9 + 5 * hf);
+            if (lane == 0) mbar_arrive(p_full);
+            XQ_TR(i < 30 && warp == 0 && lane == 0, 16 * i + 5);
+        }
+        if (hf == 0) {
+        // ---- epilogue: dV -> bf16 -> smem -> TMA store
+        mbar_wait(dkv_done, 0);
+        tc_fence_after();
+        {
+            uint8_t *so = base + AttnBwdSmem::Q;                     // every Q stage is dead
+            const uint32_t so_a = smem_u32(so);
+#pragma unroll
+            for (int c0 = 0; c0 < AT_D; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld16(tDV + lane_addr + c0, o);
+                tmem_wait_ld();
+                uint4 v0, v1;
+                v0.x = pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1]));
+                v0.y = pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3]));
+                v0.z = pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5]));
+                v0.w = pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7]));
+                v1.x = pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9]));
+                v1.y = pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11]));
+                v1.z = pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13]));
+                v1.w = pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15]));
+                sts128(so_a + rowtile_unit(krow, c0 / 8), v0);
+                sts128(so_a + rowtile_unit(krow, c0 / 8 + 1), v1);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            named_bar_sync(2, 128);
+            if (tid == 0) {
+                tma_store_3d(&tmDQKV, so, colV, k0, b);
+                bulk_commit();
+                bulk_wait<0>();
+            }
+        }
+        }
+    } else if (warp < 16) {
+        reg_inc<88>();
+        // ===== wgD (warps 8-15): dS^T = P^T o (dP^T - delta[q]); thread = (key row, query half hf): the FMA warpgroups =====
+        const int hf = (warp - 8) >> 2;
+        const uint32_t dsrow0 = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
+        for (int i = 0; i < nQ; ++i) {
+            const uint32_t dsrow = dsrow0 + (i & 1) * 2 * AT_TILE;     // double-buffered dS operand of the dQ MMA
+            const int st = i % AB_QS;
+            const int nqr = nq_of(i);
+            mbar_wait(&q_full[st], (i / AB_QS) & 1);
+            mbar_wait(p_full, i & 1);
+            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 8);
+            tc_fence_after();
+            uint32_t pk[32];                                          // this half of P^T as written by wgE: 2 bf16 per word
+            tmem_ld32(tP + lane_addr + hf * 32, pk);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_read);
+            mbar_wait(dp_full, i & 1);
+            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 9);
+            // this dS buffer was last read by the dQ_{i-2} MMA (long retired: dq_full(i-2) completed before dq_free(i-2), which the
+            // MMA warp waited for before issuing dQ_{i-1}, which precedes dP^T_i in its program order)
             tc_fence_after();
             const uint32_t d4 = smem_u32(s_delta + st * 128 + hf * 64);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t dp[16], pk[8];
-                if (ch * 16 < ncol) {
-                    tmem_ld16(tDP + lane_addr + hf * 64 + ch * 16, dp);
+            for (int ch = 0; ch < 4; ++ch) {                          // 16 queries per chunk
+                const int col = hf * 64 + ch * 16;
+                uint32_t dp[16], o8[8];
+                if (col < nqr) {
+                    tmem_ld16(tDP + lane_addr + col, dp);
                     tmem_wait_ld();
-                } else {
+                } else {                                              // beyond the block's queries: P = 0, dS = 0
 #pragma unroll
                     for (int e = 0; e < 16; ++e) dp[e] = 0u;
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const float4 Dl = lds128f(d4 + (ch * 4 + g) * 16);
-                    const int o = ch * 16 + g * 4;
-                    const float d0 = p[o + 0] * (__uint_as_float(dp[g * 4 + 0]) - Dl.x);
-                    const float d1 = p[o + 1] * (__uint_as_float(dp[g * 4 + 1]) - Dl.y);
-                    const float d2 = p[o + 2] * (__uint_as_float(dp[g * 4 + 2]) - Dl.z);
-                    const float d3 = p[o + 3] * (__uint_as_float(dp[g * 4 + 3]) - Dl.w);
-                    pk[g * 2 + 0] = pack_bf16(d0, d1);
-                    pk[g * 2 + 1] = pack_bf16(d2, d3);
+                    const uint32_t w0 = pk[ch * 8 + g * 2], w1 = pk[ch * 8 + g * 2 + 1];
+                    const float d0 = __uint_as_float(w0 << 16) * (__uint_as_float(dp[g * 4 + 0]) - Dl.x);
+                    const float d1 = __uint_as_float(w0 & 0xffff0000u) * (__uint_as_float(dp[g * 4 + 1]) - Dl.y);
+                    const float d2 = __uint_as_float(w1 << 16) * (__uint_as_float(dp[g * 4 + 2]) - Dl.z);
+                    const float d3 = __uint_as_float(w1 & 0xffff0000u) * (__uint_as_float(dp[g * 4 + 3]) - Dl.w);
+                    o8[g * 2 + 0] = pack_bf16(d0, d1);
+                    o8[g * 2 + 1] = pack_bf16(d2, d3);
                 }
-                // dS^T for the dK MMA (TMEM, over this thread's own dP^T columns) ...
+                // dS^T for the dK MMA (TMEM, over this thread's own, already consumed, dP^T columns) ...
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
-                             ::"r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]),
+                             ::"r"(o8[0]), "r"(o8[1]), "r"(o8[2]), "r"(o8[3]), "r"(o8[4]), "r"(o8[5]), "r"(o8[6]), "r"(o8[7]),
                                "r"(tDP + lane_addr + hf * 64 + ch * 8)
                              : "memory");
-                // ... and dS for the dQ MMA (smem, MN-major: row = key, 64 queries of this half along the row)
-                sts128(dsrow + rowtile_unit(krow, ch * 2), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                sts128(dsrow + rowtile_unit(krow, ch * 2 + 1), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                // ... and dS for the dQ MMA (smem, MN-major: row = key, this half's 64 queries along the row)
+                sts128(dsrow + rowtile_unit(krow, ch * 2), make_uint4(o8[0], o8[1], o8[2], o8[3]));
+                sts128(dsrow + rowtile_unit(krow, ch * 2 + 1), make_uint4(o8[4], o8[5], o8[6], o8[7]));
+                XQ_TR(i < 30 && warp == 8 && lane == 0 && ch < 3, 16 * i + 13 + ch);
             }
+            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 11);
             fence_async_smem();
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ds_full[hf]);
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 10 + 5 * hf);
+            if (lane == 0) mbar_arrive(ds_full);
+            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 10);
         }
-        drain_dq(nQ - 1);
-        XQ_TR(qd == 0 && lane == 0, 16 * 30 + hf);
-        // ---- epilogue: dV (query half 0's warps) and dK * scale (half 1's warps) -> bf16 -> smem -> TMA store
+        if (hf == 0) {
+        // ---- epilogue: dK * scale -> bf16 -> smem -> TMA store
         mbar_wait(dkv_done, 0);
         tc_fence_after();
         {
-            const uint32_t src = hf == 0 ? tDV : tDK;
-            const float mul = hf == 0 ? 1.0f : scale;
-            uint8_t *so = base + AttnBwdSmem::Q + hf * AT_TILE;      // every Q stage is dead
+            uint8_t *so = base + AttnBwdSmem::Q + AT_TILE;
             const uint32_t so_a = smem_u32(so);
 #pragma unroll
             for (int c0 = 0; c0 < AT_D; c0 += 16) {
                 uint32_t o[16];
-                tmem_ld16(src + lane_addr + c0, o);
+                tmem_ld16(tDK + lane_addr + c0, o);
                 tmem_wait_ld();
                 uint4 v0, v1;
-                v0.x = pack_bf16(__uint_as_float(o[0]) * mul, __uint_as_float(o[1]) * mul);
-                v0.y = pack_bf16(__uint_as_float(o[2]) * mul, __uint_as_float(o[3]) * mul);
-                v0.z = pack_bf16(__uint_as_float(o[4]) * mul, __uint_as_float(o[5]) * mul);
-                v0.w = pack_bf16(__uint_as_float(o[6]) * mul, __uint_as_float(o[7]) * mul);
-                v1.x = pack_bf16(__uint_as_float(o[8]) * mul, __uint_as_float(o[9]) * mul);
-                v1.y = pack_bf16(__uint_as_float(o[10]) * mul, __uint_as_float(o[11]) * mul);
-                v1.z = pack_bf16(__uint_as_float(o[12]) * mul, __uint_as_float(o[13]) * mul);
-                v1.w = pack_bf16(__uint_as_float(o[14]) * mul, __uint_as_float(o[15]) * mul);
+                v0.x = pack_bf16(__uint_as_float(o[0]) * scale, __uint_as_float(o[1]) * scale);
+                v0.y = pack_bf16(__uint_as_float(o[2]) * scale, __uint_as_float(o[3]) * scale);
+                v0.z = pack_bf16(__uint_as_float(o[4]) * scale, __uint_as_float(o[5]) * scale);
+                v0.w = pack_bf16(__uint_as_float(o[6]) * scale, __uint_as_float(o[7]) * scale);
+                v1.x = pack_bf16(__uint_as_float(o[8]) * scale, __uint_as_float(o[9]) * scale);
+                v1.y = pack_bf16(__uint_as_float(o[10]) * scale, __uint_as_float(o[11]) * scale);
+                v1.z = pack_bf16(__uint_as_float(o[12]) * scale, __uint_as_float(o[13]) * scale);
+                v1.w = pack_bf16(__uint_as_float(o[14]) * scale, __uint_as_float(o[15]) * scale);
                 sts128(so_a + rowtile_unit(krow, c0 / 8), v0);
                 sts128(so_a + rowtile_unit(krow, c0 / 8 + 1), v1);
             }
             fence_async_smem();
             tc_fence_before();
-            named_bar_sync(6 + hf, 128);
-            if (wtid == 0) {
-                tma_store_3d(&tmDQKV, so, hf == 0 ? colV : colK, k0, b);
+            named_bar_sync(3, 128);
+            if (tid == 256) {
+                tma_store_3d(&tmDQKV, so, colK, k0, b);
                 bulk_commit();
-                bulk_wait<0>();          // this warpgroup's reduce-adds and its store complete before the CTA retires
+                bulk_wait<0>();
             }
         }
+        }
+    } else {
+        reg_dec<56>();
+        // ===== wgQ (warps 20-23): dQ_i partial (TMEM lanes = queries) -> fp32 smem row tiles -> TMA reduce-add =====
+        const uint32_t stg = smem_u32(base + AttnBwdSmem::DQ);
+        const bool issuer = tid == 20 * 32;
+        for (int i = 0; i < nQ; ++i) {
+            mbar_wait(dq_full, i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int hfc = 0; hfc < 2; ++hfc) {       // 32 head-dim columns per pass through the staging tile
+                uint32_t r[32];
+                tmem_ld32(tDQ + lane_addr + hfc * 32, r);
+                tmem_wait_ld();
+                if (hfc == 1) {                       // the whole accumulator has left TMEM: the next dQ MMA may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dq_free);
+                }
+                if (issuer) bulk_wait_read<0>();     // the previous reduce has finished reading the staging tile
+                named_bar_sync(4, 128);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sts128(stg + rowtile_unit(krow, u), make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]));
+                fence_async_smem();
+                named_bar_sync(5, 128);
+                if (issuer) {
+#ifndef XQ_ATTN_EXP_NODQ      // experiment switch (tools/): time the kernel without the dQ reduce traffic
+                    tma_reduce_add_3d(&tmDQ, base + AttnBwdSmem::DQ, hfc * 32, i * AT_BM, bh);
+#endif
+                    bulk_commit();
+                }
+            }
+            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 12);
+        }
+        if (issuer) bulk_wait<0>();
     }
     __syncthreads();
     XQ_TR(tid == 0, 16 * 30 + 3);
-    if (warp == 9) {
+    if (warp == 17) {
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }

@@ -29,9 +29,9 @@ dqkv = vit_ops.attn_tc_backward(qkv, out, lse, g, H)
 torch.cuda.synchronize()
 t = trace.cpu().tolist()
 t0 = t[16 * 30 + 2]
-names = ["mma:p_full0", "mma:p_full1", "mma:ds_full0", "mma:ds_full1", "mma:dQ issued", "-", "wg0:S seen", "wg0:P done", "wg0:drain done",
-         "wg0:dP seen", "wg0:dS done", "wg1:S seen", "wg1:P done", "wg1:drain done", "wg1:dP seen", "wg1:dS done"]
-print("CTA 0 start -> end:", t[16 * 30 + 3] - t0, "clocks; compute loops end wg0", t[16 * 30] - t0, "wg1", t[16 * 30 + 1] - t0)
+names = ["mma:p_full", "mma:ds_full", "mma:dQ issued", "-", "wgE:S seen", "wgE:P done", "-", "-", "wgD:P seen", "wgD:dP seen", "wgD:dS done",
+         "wgD:chunks done", "wgQ:drained", "wgD:ch0", "wgD:ch1", "wgD:ch2"]
+print("CTA 0 start -> end:", t[16 * 30 + 3] - t0, "clocks")
 for i in range(6):
     row = [(names[k], t[16 * i + k] - t0) for k in range(16) if t[16 * i + k]]
     print(f"i={i}: " + "  ".join(f"{n}={v}" for n, v in row))

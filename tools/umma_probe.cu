@@ -189,12 +189,8 @@ __global__ void __launch_bounds__(128, 1) mma_time_kernel(int flavour, int n, in
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred;
-}
 // same measurement, but the WHOLE warp runs the loop and only the MMA is predicated by elect.sync (CUTLASS style)
+template <int flavour>
 __global__ void __launch_bounds__(128, 1) mma_time_kernel_elect(int n, int reps, long long *out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -212,12 +208,17 @@ __global__ void __launch_bounds__(128, 1) mma_time_kernel_elect(int n, int reps,
     const uint32_t tmem = *tptr;
     if (warp == 1) {
         const uint64_t ad = desc_k_sw128(smem_u32(sA)), bd = desc_k_sw128(smem_u32(sB));
-        const uint32_t id = idesc_bf16(128, n, 0, 0);
+        const uint64_t amn = desc_mn_sw128(smem_u32(sA), 16384, 1024), bmn = desc_mn_sw128(smem_u32(sB), 16384, 1024);
         long long t0 = clock64();
         for (int r = 0; r < reps; r += 4) {
             if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_ss(tmem, ad + 2 * k, bd + 2 * k, id, 1);
+                for (int k = 0; k < 4; ++k) {
+                    if (flavour == 0) umma_ss(tmem, ad + 2 * k, bd + 2 * k, idesc_bf16(128, n, 0, 0), 1);
+                    else if (flavour == 1) umma_ts(tmem, tmem + 256 + k * 8, bmn + 128 * k, idesc_bf16(128, n, 0, 1), 1);
+                    else if (flavour == 2) umma_ss(tmem, amn + 128 * k, bmn + 128 * k, idesc_bf16(128, n, 1, 1), 1);
+                    else umma_ts(tmem, tmem + 256 + k * 8, bd + 2 * k, idesc_bf16(128, n, 0, 0), 1);
+                }
             }
             __syncwarp();
         }
@@ -387,13 +388,21 @@ int main() {
     {
         long long *dout, hout[2];
         CK(cudaMalloc(&dout, 16));
-        CK(cudaFuncSetAttribute(mma_time_kernel_elect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        for (int n : {128, 64, 16})
+        CK(cudaFuncSetAttribute(mma_time_kernel_elect<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        CK(cudaFuncSetAttribute(mma_time_kernel_elect<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        CK(cudaFuncSetAttribute(mma_time_kernel_elect<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        CK(cudaFuncSetAttribute(mma_time_kernel_elect<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        struct { int fl, n; const char *name; } ec[] = {{0, 128, "SS K x K   N128"}, {0, 64, "SS K x K   N64"}, {0, 16, "SS K x K   N16"},
+            {1, 64, "TS tmem x B MN-major N64"}, {2, 64, "SS A MN x B MN N64"}, {3, 64, "TS tmem x B K-major N64"}, {3, 128, "TS tmem x B K-major N128"}};
+        for (auto &c : ec)
             for (int reps : {64, 256}) {
-                mma_time_kernel_elect<<<1, 128, SMEM>>>(n, reps, dout);
+                if (c.fl == 0) mma_time_kernel_elect<0><<<1, 128, SMEM>>>(c.n, reps, dout);
+                if (c.fl == 1) mma_time_kernel_elect<1><<<1, 128, SMEM>>>(c.n, reps, dout);
+                if (c.fl == 2) mma_time_kernel_elect<2><<<1, 128, SMEM>>>(c.n, reps, dout);
+                if (c.fl == 3) mma_time_kernel_elect<3><<<1, 128, SMEM>>>(c.n, reps, dout);
                 CK(cudaDeviceSynchronize());
                 CK(cudaMemcpy(hout, dout, 16, cudaMemcpyDeviceToHost));
-                printf("T5 elect.sync issue, SS K x K M128 N%-3d reps %3d: issue %6.1f clk/MMA, issue+drain %6.1f clk/MMA\n", n, reps,
+                printf("T5 elect.sync issue, %-28s reps %3d: issue %6.1f clk/MMA, issue+drain %6.1f clk/MMA\n", c.name, reps,
                        (double)hout[0] / reps, (double)hout[1] / reps);
             }
     }
