@@ -18,6 +18,12 @@
 
 namespace xq {
 
+static long long *g_ms_trace = nullptr;     // per-scale clock trace buffer (development builds only)
+#ifdef XQ_MS_TRACE
+extern "C" int xq_dev_set_ms_trace(void *dev_ptr) { g_ms_trace = (long long *)dev_ptr; return 0; }   // tools/ms_trace.py
+#endif
+
+
 constexpr int MS_THREADS = 384;       // forward / decode: 12 warps; the search tiling uses the first 256 threads (16 x 16)
 constexpr int MS_BWD_THREADS = 512;   // backward: no search, only latency-bound conv / pooling work -> more warps
 constexpr int MS_TILE_V = 128;
@@ -1164,8 +1170,7 @@ int xq_ms_forward(const xq_ms_desc *d, const float *f, const float *E, const flo
     a.partial = with_losses ? ws.partial : nullptr;
     a.F_last = saved ? sv.F_last : nullptr;
     a.Fprev01 = (bsq && with_losses) ? sv.Fprev01 : nullptr;
-    a.dbg = nullptr;
-    if (const char *e = getenv("XQ_MS_TRACE")) a.dbg = (long long *)strtoull(e, nullptr, 0);
+    a.dbg = g_ms_trace;          // nullptr unless a development build set it (xq_dev_set_ms_trace, -DXQ_MS_TRACE)
     XQ_CUDA_TRY(cudaFuncSetAttribute(ms_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ms_forward_kernel<<<d->B, MS_THREADS, smem, stream>>>(a);
     XQ_LAUNCH_CHECK("ms_forward_kernel");

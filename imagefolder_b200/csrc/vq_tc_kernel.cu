@@ -20,11 +20,13 @@
 // (TMEM lane quadrant = warp_id % 4).  Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA),
 // tmem_full/tmem_empty per accumulator stage (MMA <-> epilogue).
 #include <cuda.h>
-#include <cstdlib>
+#include <mutex>
 
 #include "xq_common.cuh"
 
 namespace xq {
+
+static long long *g_vq_tc_trace = nullptr;     // in-kernel clock trace buffer (development builds only)
 
 constexpr int TC_BM = 128;       // rows per CTA  (UMMA M)
 constexpr int TC_BN = 128;       // codes per tile (UMMA N); 2 accumulator stages = 256 TMEM columns -> 2 CTAs / SM
@@ -62,6 +64,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
+}
+// one lane of a CONVERGED warp: single-thread tcgen05 / TMA instructions issued under `if (lane == 0)` are wrapped by the
+// compiler in an ELECT / BRA.U.ANY serialisation loop (~112 clk per tcgen05.mma measured, tools/umma_probe.cu); issued under
+// elect.sync by a warp that runs the control flow uniformly they are plain predicated instructions (tensor-pipe rate)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -226,29 +236,30 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
     if (trace && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int t = 0; t < T; ++t) {
-                const int st = t % nstage;
-                mbar_wait(&s.empty[st], ((t / nstage) & 1) ^ 1);
+        // ===== TMA producer (whole warp runs the loop, one elected lane issues) =====
+        for (int t = 0; t < T; ++t) {
+            const int st = t % nstage;
+            mbar_wait(&s.empty[st], ((t / nstage) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&s.full[st], stage_bytes);
                 float *dst = s.B + (size_t)st * TC_BN * C;
                 for (int kc = 0; kc < KC; ++kc)
                     tma_load_2d(dst + (size_t)kc * TC_BN * 32, &tmB, kc * 32, t * TC_BN, &s.full[st]);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
-            const uint32_t a_addr = smem_u32(s.A);
-            for (int t = 0; t < T; ++t) {
-                const int st = t % nstage, as = t & 1;
-                mbar_wait(&s.tempty[as], ((t >> 1) & 1) ^ 1);
-                if (trace && t < 60) dbg[8 + 4 * t + 0] = clock64();
-                mbar_wait(&s.full[st], (t / nstage) & 1);
-                if (trace && t < 60) dbg[8 + 4 * t + 1] = clock64();
-                tc_fence_after();
+        // ===== MMA issuer (whole warp runs the control flow, one elected lane issues) =====
+        const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+        const uint32_t a_addr = smem_u32(s.A);
+        for (int t = 0; t < T; ++t) {
+            const int st = t % nstage, as = t & 1;
+            mbar_wait(&s.tempty[as], ((t >> 1) & 1) ^ 1);
+            if (trace && lane == 0 && t < 60) dbg[8 + 4 * t + 0] = clock64();
+            mbar_wait(&s.full[st], (t / nstage) & 1);
+            if (trace && lane == 0 && t < 60) dbg[8 + 4 * t + 1] = clock64();
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t b_addr = smem_u32(s.B + (size_t)st * TC_BN * C);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * TC_BN);
                 for (int kc = 0; kc < KC; ++kc) {
@@ -261,8 +272,9 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap tmB, const float *__rest
                 }
                 umma_commit(&s.empty[st]);    // smem stage free once these MMAs retire
                 umma_commit(&s.tfull[as]);    // accumulator ready
-                if (trace && t < 60) dbg[8 + 4 * t + 2] = clock64();
             }
+            __syncwarp();
+            if (trace && lane == 0 && t < 60) dbg[8 + 4 * t + 2] = clock64();
         }
     } else {
         // ===== epilogue: one thread per row (TMEM lane) =====
@@ -505,22 +517,37 @@ int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, i
     const size_t smem = tc_smem_bytes(C, nstage);
     if (smem > 227 * 1024) return XQ_ERR_UNSUPPORTED;
 
+    // the tensor map depends only on (workspace pointer, Vp, C): encode it once per distinct triple
+    struct MapEntry { const void *ptr; int Vp, C; CUtensorMap tm; };
+    static std::mutex map_mu;
+    static MapEntry map_cache[8];
+    static int map_n = 0, map_next = 0;
     CUtensorMap tm;
-    cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)Vp};
-    cuuint64_t gstr[1] = {(cuuint64_t)C * sizeof(float)};
-    cuuint32_t box[2] = {32u, (cuuint32_t)TC_BN};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)En, gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return XQ_ERR_UNSUPPORTED;
+    {
+        std::lock_guard<std::mutex> g(map_mu);
+        bool hit = false;
+        for (int i = 0; i < map_n && !hit; ++i)
+            if (map_cache[i].ptr == (const void *)En && map_cache[i].Vp == Vp && map_cache[i].C == C) { tm = map_cache[i].tm; hit = true; }
+        if (!hit) {
+            cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)Vp};
+            cuuint64_t gstr[1] = {(cuuint64_t)C * sizeof(float)};
+            cuuint32_t box[2] = {32u, (cuuint32_t)TC_BN};
+            cuuint32_t estr[2] = {1u, 1u};
+            CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)En, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return XQ_ERR_UNSUPPORTED;
+            map_cache[map_next] = MapEntry{(const void *)En, Vp, C, tm};
+            map_next = (map_next + 1) % 8;
+            if (map_n < 8) ++map_n;
+        }
+    }
 
     codebook_prep_rowmajor_kernel<<<(Vp + 127) / 128, 128, 0, stream>>>(E, V, C, Vp, En, ee);
     XQ_LAUNCH_CHECK("codebook_prep_rowmajor_kernel");
     XQ_CUDA_TRY(cudaFuncSetAttribute(vq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas = (N + TC_BM - 1) / TC_BM;
-    long long *dbg = nullptr;
-    if (const char *e = getenv("XQ_VQ_TC_TRACE")) dbg = (long long *)strtoull(e, nullptr, 0);  // device pointer (dev tool)
+    long long *dbg = g_vq_tc_trace;          // nullptr unless a development build set it (xq_dev_set_vq_trace, -DXQ_VQ_TC_TRACE)
     vq_search_tc_kernel<<<ctas, TC_THREADS, smem, stream>>>(tm, z, E, En, ee, N, C, HW, V, Vp, nstage, ste_value, idx, out,
                                                            loss ? partial : nullptr, hist, dbg);
     XQ_LAUNCH_CHECK("vq_search_tc_kernel");
@@ -530,5 +557,9 @@ int vq_tc_forward(const float *z, const float *E, int B, int C, int HW, int V, i
     }
     return XQ_OK;
 }
+
+#ifdef XQ_VQ_TC_TRACE
+extern "C" int xq_dev_set_vq_trace(void *dev_ptr) { xq::g_vq_tc_trace = (long long *)dev_ptr; return 0; }   // tools/vq_tc_trace.py
+#endif
 
 }  // namespace xq

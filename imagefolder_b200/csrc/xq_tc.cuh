@@ -40,6 +40,19 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// non-blocking poll (try_wait may put the thread to sleep for an implementation-defined time before answering "not yet";
+// an event loop that polls several barriers must not pay that for every barrier that is not ready)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try(bar, parity)) {}
 }

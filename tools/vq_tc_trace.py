@@ -1,13 +1,17 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from imagefolder_b200 import ops
+from imagefolder_b200 import _capi as C, ops
 V, C, B = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (8192, 32, 256)
 z = torch.randn(B, C, 16, 16, device="cuda")
 E = torch.nn.functional.normalize(torch.randn(V, C, device="cuda"), dim=-1)
 os.environ["XQ_VQ_ALGO"] = "tc"
 for _ in range(3): ops.vq_lookup(z, E, True)
 dbg = torch.zeros(512, dtype=torch.int64, device="cuda")
-os.environ["XQ_VQ_TC_TRACE"] = str(dbg.data_ptr())
+# needs a development build of the library: add -DXQ_VQ_TC_TRACE to the nvcc flags of csrc/build.sh
+import ctypes
+_L = C.lib()
+_L.xq_dev_set_vq_trace.argtypes = [ctypes.c_void_p]
+_L.xq_dev_set_vq_trace(dbg.data_ptr())
 ops.vq_lookup(z, E, True)
 torch.cuda.synchronize()
 d = dbg.cpu().tolist()
