@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the MSVR10P2-4096 ours-vs-eager extra measurement")
+    p.add_argument("--fp32-grads", action="store_true", help="multi-GPU: all-reduce fp32 gradient buckets (stock DDP) instead of bf16")
     p.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline step (0 = auto)")
     return p.parse_args()
 
@@ -176,7 +177,16 @@ def make_step(ctx, workload, B, impl):
     if impl == "eager":
         from oracle.eager_ref import EagerTokenizer   # baseline leg only: reference-style eager ops, no libxqb200
         fwd_module = EagerTokenizer(model)
-    net = (torch.nn.parallel.DistributedDataParallel(fwd_module, device_ids=[ctx.local]) if ctx.world > 1 else fwd_module)
+    net = fwd_module
+    if ctx.world > 1:
+        # gradients are the only collective on the critical path.  bf16 buckets halve the bytes NCCL moves
+        # through the HBM the glue kernels are streaming from (the master weights / AdamW state stay fp32); `--fp32-grads`
+        # restores stock DDP.  The eager arm keeps stock DDP: it is the reference's configuration (xqgan_train.py:412).
+        net = torch.nn.parallel.DistributedDataParallel(fwd_module, device_ids=[ctx.local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=100)
+        if impl == "ours" and not getattr(ctx, "fp32_grads", False):
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW(model.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
     alpha, beta, delta = xcfg.perturbation_schedule(margs, 0)
 
@@ -319,6 +329,7 @@ def run_ours(a):
     import gc
     from imagefolder_b200 import _capi, vit_ops
     ctx = Ctx()
+    ctx.fp32_grads = a.fp32_grads
     world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
     model, margs, step, imgs_dev = make_step(ctx, a.workload, a.batch, a.impl)
     B = a.batch
@@ -420,6 +431,7 @@ def run_ours(a):
         "config": {"workload": f"{a.workload} tokenizer training step, per-GPU batch {B}, 256x256, ViT-B enc/dec, "
                                "fwd+bwd+AdamW, L2+vq+commit loss (no LPIPS/GAN/teacher)",
                    "global_batch": world * B, "parallelism": f"dp{world}",
+                   "grad_allreduce": ("none (1 GPU)" if world == 1 else ("fp32 buckets" if a.fp32_grads else "bf16-compressed buckets (fp32 master weights)")),
                    "l2_policy": "inputs (201 MB/step) + activations exceed the 126 MB L2"},
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": imgs_host.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,

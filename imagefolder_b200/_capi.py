@@ -114,7 +114,7 @@ def lib() -> ctypes.CDLL:
     L.xq_vit_attn_bwd_workspace_bytes.restype = c_size_t
     L.xq_vit_attn_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.xq_vit_attn_bwd.restype = c_int
-    L.xq_vit_attn_bwd.argtypes = [vp, vp, vp, f32p, vp, c_int, c_int, c_int, c_int, c_float, vp, c_size_t, vp]
+    L.xq_vit_attn_bwd.argtypes = [vp, vp, vp, f32p, vp, f32p, c_int, c_int, c_int, c_int, c_float, vp, c_size_t, vp]
     L.xq_lpips_workspace_bytes.restype = c_size_t
     L.xq_lpips_workspace_bytes.argtypes = [c_int, c_int]
     L.xq_lpips_layer_forward.restype = c_int

@@ -497,8 +497,8 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmDQ,
-                const float *__restrict__ lseP, const float *__restrict__ deltaP, int N, int H, int nK, int Npad, float c,
-                float scale) {
+                const float *__restrict__ lseP, const float *__restrict__ deltaP, float *__restrict__ g_bias, int N, int H, int nK,
+                int Npad, float c, float scale) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
@@ -740,8 +740,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (tid == 0) {
                 tma_store_3d(&tmDQKV, so, colV, k0, b);
                 bulk_commit();
-                bulk_wait<0>();
             }
+            if (g_bias && tid < AT_D) {               // qkv-bias gradient: column sums of the (bf16-rounded) tile, valid key rows only
+                const int rows = min(AT_BN, N - k0);
+                float acc = 0.f;
+                for (int r = 0; r < rows; ++r) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(so + rowtile_off_bf16(r, tid)));
+                atomicAdd(g_bias + colV + tid, acc);
+            }
+            if (tid == 0) bulk_wait<0>();
         }
         }
     } else if (warp < 16) {
@@ -839,8 +845,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (tid == 256) {
                 tma_store_3d(&tmDQKV, so, colK, k0, b);
                 bulk_commit();
-                bulk_wait<0>();
             }
+            if (g_bias && tid - 256 < AT_D) {
+                const int cidx = tid - 256, rows = min(AT_BN, N - k0);
+                float acc = 0.f;
+                for (int r = 0; r < rows; ++r) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(so + rowtile_off_bf16(r, cidx)));
+                atomicAdd(g_bias + colK + cidx, acc);
+            }
+            if (tid == 256) bulk_wait<0>();
         }
         }
     } else {
@@ -924,26 +936,50 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ out, cons
     }
 }
 
-// dq_acc fp32 [B*H][N][64] * scale -> dqkv[b][n][0][h][:] bf16
-__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, __nv_bfloat16 *__restrict__ dqkv, int B, int N, int H,
-                                       float scale) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 8 values
-    const long long total = (long long)B * H * N * 8;
-    if (gid >= total) return;
-    const int part = (int)(gid & 7);
-    const long long rowid = gid >> 3;           // (bh, n)
-    const int n = (int)(rowid % N);
-    const long long bhh = rowid / N;
-    const int hh = (int)(bhh % H);
-    const int bb = (int)(bhh / H);
-    const float4 x0 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
-    const float4 x1 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
-    uint4 o;
-    o.x = pack_bf16(x0.x * scale, x0.y * scale);
-    o.y = pack_bf16(x0.z * scale, x0.w * scale);
-    o.z = pack_bf16(x1.x * scale, x1.y * scale);
-    o.w = pack_bf16(x1.z * scale, x1.w * scale);
-    *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
+// dq_acc fp32 [B*H][N][64] * scale -> dqkv[b][n][0][h][:] bf16 ; optionally the q-part of the qkv-bias gradient (column sums of
+// the rounded values).  grid = (ceil(N / 32), B*H), 256 threads = 32 rows x 8 column groups: a block never mixes heads.
+__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias,
+                                       int N, int H, float scale) {
+    __shared__ float red[8][AT_D];
+    const int part = threadIdx.x & 7, rloc = threadIdx.x >> 3;
+    const int bhh = blockIdx.y, n = blockIdx.x * 32 + rloc;
+    const int hh = bhh % H, bb = bhh / H;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (n < N) {
+        const size_t rowid = (size_t)bhh * N + n;
+        const float4 x0 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
+        const float4 x1 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
+        uint4 o;
+        o.x = pack_bf16(x0.x * scale, x0.y * scale);
+        o.y = pack_bf16(x0.z * scale, x0.w * scale);
+        o.z = pack_bf16(x1.x * scale, x1.y * scale);
+        o.w = pack_bf16(x1.z * scale, x1.w * scale);
+        *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
+        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+    }
+    if (!g_bias) return;
+    // rows of a warp: lanes with equal `part` are 8 apart -> xor-shuffle over 8, 16; then 8 warps through shared memory
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = v[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < AT_D) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) acc += red[w8][threadIdx.x];
+        atomicAdd(g_bias + hh * AT_D + threadIdx.x, acc);
+    }
 }
 
 struct AttnBwdMaps {
@@ -999,8 +1035,8 @@ size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H) {
     return xq::attn_bwd_ws_layout(B, N, H, nullptr, nullptr);
 }
 
-int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, int B, int N, int H,
-                    int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream) {
+int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, float *g_bias, int B, int N,
+                    int H, int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace xq;
     if (!qkv || !out || !d_out || !lse2 || !dqkv || !workspace || B <= 0 || N <= 0 || H <= 0) return XQ_ERR_ARG;
     if (head_dim != AT_D) return XQ_ERR_UNSUPPORTED;
@@ -1017,6 +1053,7 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     const int nK = (N + AT_BN - 1) / AT_BN;
     const int Npad = (N + AT_BM - 1) / AT_BM * AT_BM;
     XQ_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * H * N * AT_D * sizeof(float), st));
+    if (g_bias) XQ_CUDA_TRY(cudaMemsetAsync(g_bias, 0, (size_t)3 * H * AT_D * sizeof(float), st));
     {
         const long long threads = (long long)B * H * Npad * 8;
         attn_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16 *)out, (const __nv_bfloat16 *)d_out,
@@ -1031,12 +1068,13 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     }
     const long long ctas = (long long)B * H * nK;
     if (ctas > 0x7fffffffLL) return XQ_ERR_ARG;
-    attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, N, H, nK, Npad,
+    attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, g_bias, N, H, nK, Npad,
                                                               scale * 1.4426950408889634f, scale);
     XQ_LAUNCH_CHECK("attn_bwd_kernel");
     {
-        const long long threads = (long long)B * H * N * 8;
-        attn_dq_convert_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(acc, (__nv_bfloat16 *)dqkv, B, N, H, scale);
+        if ((long long)B * H > 65535) return XQ_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)(B * H));
+        attn_dq_convert_kernel<<<grid, 256, 0, st>>>(acc, (__nv_bfloat16 *)dqkv, g_bias, N, H, scale);
         XQ_LAUNCH_CHECK("attn_dq_convert_kernel");
     }
     return XQ_OK;

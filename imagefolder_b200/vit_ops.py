@@ -144,13 +144,15 @@ def attn_tc_forward(qkv, num_heads: int):
 _ATTN_WS = {}
 
 
-def attn_tc_backward(qkv, out, lse2, g, num_heads: int):
-    """d(out) bf16 [B,N,H*64] -> d(qkv) bf16 [B,N,3*H*64] written directly in the packed layout."""
+def attn_tc_backward(qkv, out, lse2, g, num_heads: int, want_bias_grad: bool = False):
+    """d(out) bf16 [B,N,H*64] -> d(qkv) bf16 [B,N,3*H*64] written directly in the packed layout
+    (+ its column sums = the qkv-bias gradient, fp32 [3*H*64], when asked for)."""
     B, N, C3 = qkv.shape
     g = g.contiguous()
     if g.dtype != torch.bfloat16:
         g = g.to(torch.bfloat16)
     dqkv = torch.empty_like(qkv)
+    db = torch.empty(C3, dtype=torch.float32, device=qkv.device) if want_bias_grad else None
     L = _lib()
     nbytes = int(L.xq_vit_attn_bwd_workspace_bytes(B, N, num_heads))
     key = (qkv.device.index, torch.cuda.current_stream(qkv.device).cuda_stream)
@@ -158,9 +160,9 @@ def attn_tc_backward(qkv, out, lse2, g, num_heads: int):
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _ATTN_WS[key] = ws
-    _call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, _ptr(qkv), _ptr(out), _ptr(g), _ptr(lse2), _ptr(dqkv), B, N, num_heads, 64,
-          0.125, _ptr(ws), ws.numel(), _stream(qkv.device), nbytes=qkv.numel() * 4 + out.numel() * 4 + lse2.numel() * 4)
-    return dqkv
+    _call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, _ptr(qkv), _ptr(out), _ptr(g), _ptr(lse2), _ptr(dqkv), _ptr(db), B, N, num_heads,
+          64, 0.125, _ptr(ws), ws.numel(), _stream(qkv.device), nbytes=qkv.numel() * 4 + out.numel() * 4 + lse2.numel() * 4)
+    return (dqkv, db) if want_bias_grad else dqkv
 
 
 def _sdpa_packed(qkv, num_heads, dropout_p):
@@ -263,8 +265,10 @@ class _QKVAttention(torch.autograd.Function):
         B, N, C = ctx.dims
         if ctx.tc:
             y, Wb, qkv, out, lse2 = ctx.saved_tensors
-            dqkv = attn_tc_backward(qkv, out, lse2, g, ctx.heads)
-            db = dqkv.view(B * N, 3 * C).sum(0, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+            if ctx.needs_input_grad[2]:
+                dqkv, db = attn_tc_backward(qkv, out, lse2, g, ctx.heads, want_bias_grad=True)
+            else:
+                dqkv, db = attn_tc_backward(qkv, out, lse2, g, ctx.heads), None
         else:
             inner, ctx.inner = ctx.inner, None
             y, Wb = ctx.saved_tensors

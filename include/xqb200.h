@@ -245,10 +245,11 @@ int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H
 /*   Backward of xq_vit_attn_fwd: d_out bf16 [B,N,H*64] -> dqkv bf16 [B,N,3,H,64] (the gradient of the packed projection,
  *   written in place of autograd's three permuted tensors + stack).  `out` and `lse2` are the forward's results.
  *   workspace (256-byte aligned, xq_vit_attn_bwd_workspace_bytes): fp32 dQ accumulator [B*H,N,64] (TMA reduce-add across
- *   the key blocks) + the padded statistics.  3 launches + 1 memset. */
+ *   the key blocks) + the padded statistics.  g_bias fp32 [3*H*64] (may be NULL) receives the column sums of dqkv = the
+ *   gradient of the qkv bias (nn.Linear's backward `sum(0)` pass, fused into the epilogues).  3 launches + memsets. */
 size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H);
-int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, int B, int N, int H,
-                    int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream);
+int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, float *g_bias, int B, int N,
+                    int H, int head_dim, float scale, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * ---- loss stack -------------------------------------------------------------------

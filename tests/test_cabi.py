@@ -139,6 +139,6 @@ def test_attention_entry_points_validate_arguments_without_gpu():
     assert L.xq_vit_attn_bwd_workspace_bytes(0, 16, 1) == 0
     need = L.xq_vit_attn_bwd_workspace_bytes(2, 513, 12)
     assert need >= 2 * 12 * 513 * 64 * 4 + 2 * 2 * 12 * 640 * 4
-    assert L.xq_vit_attn_bwd(None, None, None, None, None, 1, 16, 1, 64, 0.125, None, 0, None) == -1
-    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, 2, 513, 12, 64, 0.125, 4096, need - 1, None) == -2   # workspace
-    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, 2, 513, 12, 128, 0.125, 4096, need, None) == -4
+    assert L.xq_vit_attn_bwd(None, None, None, None, None, None, 1, 16, 1, 64, 0.125, None, 0, None) == -1
+    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, None, 2, 513, 12, 64, 0.125, 4096, need - 1, None) == -2   # workspace
+    assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, None, 2, 513, 12, 128, 0.125, 4096, need, None) == -4

@@ -53,6 +53,29 @@ def _worker(rank, world, port, q):
         # torch.distributed.nn.all_gather's backward sums the gradient over ranks: each rank's loss is the same
         # global loss, so the local slice of d(loss)/d(features) is world x the single-process gradient
         np.testing.assert_allclose(a.grad.numpy(), world * a1.grad[rank * 4:(rank + 1) * 4].numpy(), rtol=1e-5, atol=1e-7)
+        # rFID data path (xqgan_train.py:517-535): uint8 NHWC conversion + rank-major all-gather of reconstructions and ground truth
+        from imagefolder_b200.evaluate import reconstruct_for_fid, to_uint8_nhwc
+
+        class _Identity(torch.nn.Module):                # stands in for VQModel: the loop only needs img_to_reconstructed_img
+            def __init__(self):
+                super().__init__()
+                self.w = torch.nn.Parameter(torch.zeros(1))
+
+            def img_to_reconstructed_img(self, x):
+                return x * 0.5
+
+        gi = torch.Generator().manual_seed(100 + rank)
+        batches = [(torch.rand(3, 3, 4, 4, generator=gi) * 2 - 1, None) for _ in range(2)]
+        m = _Identity().train()
+        smp, gt_, tot = reconstruct_for_fid(m, batches, device="cpu")
+        assert m.training and tot == 2 * 3 * world and smp.dtype == np.uint8 and smp.shape == (tot, 4, 4, 3)
+        ref_batches = []
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            ref_batches.append([torch.rand(3, 3, 4, 4, generator=gr) * 2 - 1 for _ in range(2)])
+        want_gt = np.concatenate([np.concatenate([to_uint8_nhwc(ref_batches[r][bi]).numpy() for r in range(world)]) for bi in range(2)])
+        want_s = np.concatenate([np.concatenate([to_uint8_nhwc(ref_batches[r][bi] * 0.5).numpy() for r in range(world)]) for bi in range(2)])
+        assert np.array_equal(gt_, want_gt) and np.array_equal(smp, want_s)
         # rank-dependent synthetic data seeds (bench.py) differ
         g2 = torch.Generator().manual_seed(1234 * world + rank)
         q.put((rank, float(torch.rand(1, generator=g2))))

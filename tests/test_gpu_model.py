@@ -168,3 +168,38 @@ def test_full_training_iteration_with_loss_stack(name):
     assert not torch.equal(enc_before, model.encoder.latent_tokens.detach())
     assert any(not torch.equal(a, b.detach()) for a, b in zip(head_before, vq_loss.discriminator.heads.parameters()))
     assert not any(p.requires_grad for p in vq_loss.discriminator.dino_proxy[0].parameters())   # frozen backbone
+
+
+def test_cnn_encoder_decoder_match_reference_golden_on_gpu():
+    """row a13 on the device: the conv Encoder / Decoder (xqgan_model.py:454-584) with the reference's weights reproduce the
+    reference's outputs (fp32, TF32 off; library conv / GroupNorm / attention kernels -- no hand-written kernel on this row)."""
+    from conftest import load_golden
+    from imagefolder_b200.cnn import Decoder, Encoder
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = load_golden("cnn_small")
+    enc = Encoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    dec = Decoder(ch=32, ch_mult=(1, 2), num_res_blocks=1, z_channels=8).eval()
+    enc.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("enc.")}, strict=True)
+    dec.load_state_dict({k[4:]: torch.tensor(v) for k, v in g.items() if k.startswith("dec.")}, strict=True)
+    enc, dec = enc.cuda(), dec.cuda()
+    with torch.no_grad():
+        np.testing.assert_allclose(npy(enc(torch.tensor(g["x"]).cuda())), g["h"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(npy(dec(torch.tensor(g["z"]).cuda())), g["y"], rtol=1e-3, atol=1e-4)
+
+
+def test_rfid_reconstruction_loop_on_gpu():
+    """f-2 remainder: the evaluation data path of xqgan_train.py:517-535 (eval mode, reconstruct, uint8 NHWC, gather) on the
+    CUDA tokenizer; single process here, the world_size-2 gather is covered by tests/test_dist_cpu.py."""
+    from imagefolder_b200.evaluate import reconstruct_for_fid, to_uint8_nhwc
+    model, _ = small_model("MSVR10P2-4096")
+    model = model.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.rand(2, 3, 256, 256, generator=g) * 2 - 1, torch.zeros(2)) for _ in range(2)]
+    smp, gt, tot = reconstruct_for_fid(model, batches)
+    assert model.training and tot == 4 and smp.shape == (4, 256, 256, 3) and smp.dtype == np.uint8
+    model.eval()
+    with torch.no_grad():
+        want = torch.cat([to_uint8_nhwc(model.img_to_reconstructed_img(x.cuda())) for x, _ in batches]).cpu().numpy()
+    assert np.array_equal(smp, want)
+    assert np.array_equal(gt, torch.cat([to_uint8_nhwc(x) for x, _ in batches]).numpy())

@@ -38,7 +38,7 @@ def ours_bwd(qkv, out, lse, do, H):
     dqkv = torch.empty_like(qkv)
     L = C.lib()
     ws = torch.empty(int(L.xq_vit_attn_bwd_workspace_bytes(B, N, H)), dtype=torch.uint8, device=qkv.device)
-    C.call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, C.ptr(qkv), C.ptr(out), C.ptr(do), C.ptr(lse), C.ptr(dqkv), B, N, H, 64,
+    C.call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, C.ptr(qkv), C.ptr(out), C.ptr(do), C.ptr(lse), C.ptr(dqkv), None, B, N, H, 64,
            0.125, C.ptr(ws), ws.numel(), C.stream_ptr(qkv.device))
     return dqkv
 
