@@ -629,3 +629,76 @@ def test_msvr_unscreened_seed_counts_mismatches_on_gpu():
     assert diverged <= 1
     if diverged == 0:
         close(fhat[:, :, ::2, ::2], g["fhat_sub"])
+
+
+# ------------------------------------------------------------------------------------------
+# torch.library registration: torch.compile(fullgraph=True) and CUDA-graph capture
+# ------------------------------------------------------------------------------------------
+def test_vq_custom_ops_compile_fullgraph_and_cuda_graph():
+    from imagefolder_b200 import VectorQuantizer
+    rng = np.random.default_rng(5)
+    V, C, B, hw = 512, 32, 4, 8
+    E = (rng.standard_normal((V, C)) * 0.3).astype(np.float32)
+    zs = [rng.standard_normal((B, C, hw, hw)).astype(np.float32) for _ in range(3)]
+
+    def make(custom):
+        q = VectorQuantizer(V, C).cuda().train()
+        q.embedding.weight.data.copy_(dev(E))
+        q.use_custom_ops = custom
+        return q
+
+    # (1) eager custom-op path == autograd.Function path, bit for bit, over several steps (EMA schedule on the device counter)
+    qa, qb = make(False), make(True)
+    for z in zs:
+        za, zb = dev(z, grad=True), dev(z, grad=True)
+        oa, ua, va, ca, _ = qa(za)
+        ob, ub, vb, cb, _ = qb(zb)
+        (oa.sum() * 0.3 + va + ca).backward()
+        (ob.sum() * 0.3 + vb + cb).backward()
+        assert torch.equal(oa, ob) and torch.equal(qa.last_idx, qb.last_idx) and float(va) == float(vb) and float(ca) == float(cb)
+        assert torch.equal(za.grad, zb.grad) and torch.equal(qa.embedding.weight.grad, qb.embedding.weight.grad)
+        assert torch.equal(qa.ema_vocab_hit_SV, qb.ema_vocab_hit_SV) and float(ua[0]) == float(ub[0])
+        qa.embedding.weight.grad = None
+        qb.embedding.weight.grad = None
+    assert int(qb._record_hit_dev[0]) == 3 and qa.record_hit == 3
+
+    # (2) torch.compile(fullgraph=True): no graph breaks, same numbers
+    qc = make(True)
+    fn = torch.compile(lambda zz: qc(zz)[0:4], fullgraph=True, backend="aot_eager")
+    qd = make(True)
+    for z in zs:
+        oc, uc, vc, cc = fn(dev(z, grad=True))
+        od, ud, vd, cd, _ = qd(dev(z, grad=True))
+        assert torch.equal(oc, od) and float(vc) == float(vd) and float(uc[0]) == float(ud[0])
+    assert torch.equal(qc.ema_vocab_hit_SV, qd.ema_vocab_hit_SV)
+
+    # (3) CUDA-graph capture of forward + backward of the quantizer (static buffers; replay == eager)
+    qg = make(True)
+    z_static = dev(zs[0], grad=True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):                      # warm-up on a side stream (allocations, lazy initialisation)
+        o, u, v, c, _ = qg(z_static)
+        (o.sum() * 0.3 + v + c).backward()
+    torch.cuda.current_stream().wait_stream(s)
+    qg2 = make(True)
+    qg.load_state_dict(qg2.state_dict())
+    qg._record_hit_dev.zero_()
+    z_static.grad = None
+    qg.embedding.weight.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o, u, v, c, _ = qg(z_static)
+        (o.sum() * 0.3 + v + c).backward()
+    qe = make(True)
+    for z in zs:
+        z_static.data.copy_(dev(z))
+        graph.replay()
+        ze = dev(z, grad=True)
+        oe, ue, ve, ce, _ = qe(ze)
+        qe.embedding.weight.grad = None
+        (oe.sum() * 0.3 + ve + ce).backward()
+        torch.cuda.synchronize()
+        assert torch.equal(o, oe) and float(v) == float(ve) and torch.equal(z_static.grad, ze.grad)
+        assert torch.equal(qg.embedding.weight.grad, qe.embedding.weight.grad)
+    assert torch.equal(qg.ema_vocab_hit_SV, qe.ema_vocab_hit_SV)
