@@ -936,14 +936,97 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ out, cons
     }
 }
 
-// dq_acc fp32 [B*H][N][64] * scale -> dqkv[b][n][0][h][:] bf16 ; optionally the q-part of the qkv-bias gradient (column sums of
-// the rounded values).  grid = (ceil(N / 32), B*H), 256 threads = 32 rows x 8 column groups: a block never mixes heads.
-__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias,
-                                       int N, int H, float scale) {
+// The last (N mod 128) keys when they are few (<= AB_KTAIL_MAX; 513 = 4*128 + 1): a whole CTA of attn_bwd_kernel -- five query
+// blocks of full-size MMAs -- for one or two key rows is 20 % of that kernel's work at N = 513.  Here instead: one CTA per
+// (batch, head), one warp per query (lanes own 2 of the 64 head dims), CUDA cores:
+//     s = c q.k_t ; p = exp2(s - L2[q]) ; dp = dO[q].v_t ; ds = p (dp - delta[q])
+//     dV[t] += p dO[q] ; dK[t] += ds q   (registers, reduced across the 8 warps at the end) ; ds[q][t] -> dsT for the dQ side,
+// which attn_dq_convert_kernel folds in as  dQ[q] += sum_t ds[q][t] k_t  while it converts the accumulator anyway.
+constexpr int AB_KTAIL_MAX = 16;
+
+__global__ void __launch_bounds__(256)
+attn_bwd_ktail_kernel(const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ dout, const float *__restrict__ lseP,
+                      const float *__restrict__ deltaP, __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ dsT,
+                      float *__restrict__ g_bias, int N, int H, int n0, int nt, int Npad, float c, float scale) {
+    __shared__ float2 sk[AB_KTAIL_MAX][32], sv[AB_KTAIL_MAX][32];          // tail key / value rows, [t][lane] = dims 2*lane, 2*lane+1
+    __shared__ float accs[2][AB_KTAIL_MAX][AT_D];                            // dK, dV sums over the CTA
+    const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t W = (size_t)3 * H * AT_D;
+    const __nv_bfloat16 *base_b = qkv + (size_t)b * N * W;
+    for (int i = threadIdx.x; i < nt * 32; i += 256) {
+        const int t = i >> 5, l = i & 31;
+        const __nv_bfloat16 *kr = base_b + (size_t)(n0 + t) * W + (H + h) * AT_D + 2 * l;
+        sk[t][l] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kr));
+        sv[t][l] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kr + (size_t)H * AT_D));
+    }
+    for (int i = threadIdx.x; i < 2 * AB_KTAIL_MAX * AT_D; i += 256) (&accs[0][0][0])[i] = 0.f;
+    __syncthreads();
+    float2 aK[AB_KTAIL_MAX], aV[AB_KTAIL_MAX];
+#pragma unroll
+    for (int t = 0; t < AB_KTAIL_MAX; ++t) { aK[t] = make_float2(0.f, 0.f); aV[t] = make_float2(0.f, 0.f); }
+    const float *L = lseP + (size_t)bh * Npad, *Dl = deltaP + (size_t)bh * Npad;
+    for (int q = warp; q < N; q += 8) {
+        const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(base_b + (size_t)q * W + h * AT_D + 2 * lane));
+        const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(dout + ((size_t)b * N + q) * H * AT_D + h * AT_D + 2 * lane));
+        const float lq = L[q], dq_ = Dl[q];
+#pragma unroll
+        for (int t = 0; t < AB_KTAIL_MAX; ++t) {
+            if (t < nt) {
+                float ps = fmaf(qv.x, sk[t][lane].x, qv.y * sk[t][lane].y);
+                float pd = fmaf(gv.x, sv[t][lane].x, gv.y * sv[t][lane].y);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                    pd += __shfl_xor_sync(0xffffffffu, pd, o);
+                }
+                const float p = ex2_approx(fmaf(ps, c, -lq));
+                const float ds = p * (pd - dq_);
+                aV[t].x = fmaf(p, gv.x, aV[t].x); aV[t].y = fmaf(p, gv.y, aV[t].y);
+                aK[t].x = fmaf(ds, qv.x, aK[t].x); aK[t].y = fmaf(ds, qv.y, aK[t].y);
+                if (lane == 0) dsT[((size_t)bh * N + q) * nt + t] = ds;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < AB_KTAIL_MAX; ++t) {
+        if (t < nt) {
+            atomicAdd(&accs[0][t][2 * lane], aK[t].x); atomicAdd(&accs[0][t][2 * lane + 1], aK[t].y);
+            atomicAdd(&accs[1][t][2 * lane], aV[t].x); atomicAdd(&accs[1][t][2 * lane + 1], aV[t].y);
+        }
+    }
+    __syncthreads();
+    // write the dK (scaled) / dV rows of the tail keys into the packed gradient (+ their share of the qkv-bias gradient)
+    for (int i = threadIdx.x; i < 2 * nt * AT_D; i += 256) {
+        const int which = i / (nt * AT_D), r = i - which * nt * AT_D, t = r / AT_D, d = r - t * AT_D;
+        const __nv_bfloat16 val = __float2bfloat16(accs[which][t][d] * (which == 0 ? scale : 1.0f));
+        dqkv[((size_t)b * N + n0 + t) * W + ((which == 0 ? 1 : 2) * H + h) * AT_D + d] = val;
+    }
+    if (g_bias && threadIdx.x < 2 * AT_D) {
+        const int which = threadIdx.x / AT_D, d = threadIdx.x - which * AT_D;
+        float sum = 0.f;
+        for (int t = 0; t < nt; ++t) sum += __bfloat162float(__float2bfloat16(accs[which][t][d] * (which == 0 ? scale : 1.0f)));
+        atomicAdd(g_bias + ((which == 0 ? 1 : 2) * H + h) * AT_D + d, sum);
+    }
+}
+
+// dq_acc fp32 [B*H][N][64] (+ the tail keys' contribution sum_t ds[q][t] k_t) * scale -> dqkv[b][n][0][h][:] bf16 ; optionally the
+// q-part of the qkv-bias gradient (column sums of the rounded values).  grid = (ceil(N / 32), B*H), 256 threads = 32 rows x 8
+// column groups: a block never mixes heads.
+__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ dsT,
+                                       __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias, int N, int H, int n0, int nt, float scale) {
     __shared__ float red[8][AT_D];
+    __shared__ float skt[AB_KTAIL_MAX][AT_D];
     const int part = threadIdx.x & 7, rloc = threadIdx.x >> 3;
     const int bhh = blockIdx.y, n = blockIdx.x * 32 + rloc;
     const int hh = bhh % H, bb = bhh / H;
+    if (nt > 0) {
+        for (int i = threadIdx.x; i < nt * AT_D; i += 256) {
+            const int t = i / AT_D, d = i - t * AT_D;
+            skt[t][d] = __bfloat162float(qkv[(((size_t)bb * N + n0 + t) * 3 * H + H + hh) * AT_D + d]);
+        }
+        __syncthreads();
+    }
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -951,11 +1034,17 @@ __global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, __nv_bf
         const size_t rowid = (size_t)bhh * N + n;
         const float4 x0 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
         const float4 x1 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
+        float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        for (int t = 0; t < nt; ++t) {
+            const float ds = dsT[rowid * nt + t];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = fmaf(ds, skt[t][part * 8 + e], x[e]);
+        }
         uint4 o;
-        o.x = pack_bf16(x0.x * scale, x0.y * scale);
-        o.y = pack_bf16(x0.z * scale, x0.w * scale);
-        o.z = pack_bf16(x1.x * scale, x1.y * scale);
-        o.w = pack_bf16(x1.z * scale, x1.w * scale);
+        o.x = pack_bf16(x[0] * scale, x[1] * scale);
+        o.y = pack_bf16(x[2] * scale, x[3] * scale);
+        o.z = pack_bf16(x[4] * scale, x[5] * scale);
+        o.w = pack_bf16(x[6] * scale, x[7] * scale);
         *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
         const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -1010,13 +1099,21 @@ static bool get_bwd_maps(const void *qkv, const void *dout, void *dqkv, void *ac
     return true;
 }
 
-static size_t attn_bwd_ws_layout(int B, int N, int H, size_t *off_lse, size_t *off_delta) {
+// keys handled by attn_bwd_ktail_kernel instead of a key block of attn_bwd_kernel (0 = none)
+static int attn_bwd_ktail(int N) {
+    const int r = N % AT_BN;
+    return (N > AT_BN && r != 0 && r <= AB_KTAIL_MAX) ? r : 0;
+}
+
+static size_t attn_bwd_ws_layout(int B, int N, int H, size_t *off_lse, size_t *off_delta, size_t *off_dst) {
     const size_t Npad = ((size_t)N + AT_BM - 1) / AT_BM * AT_BM;
     const size_t acc = align_up((size_t)B * H * N * AT_D * sizeof(float), 1024);
     const size_t st = align_up((size_t)B * H * Npad * sizeof(float), 1024);
+    const size_t dst = align_up((size_t)B * H * N * attn_bwd_ktail(N) * sizeof(float), 1024);
     if (off_lse) *off_lse = acc;
     if (off_delta) *off_delta = acc + st;
-    return acc + 2 * st;
+    if (off_dst) *off_dst = acc + 2 * st;
+    return acc + 2 * st + dst;
 }
 
 }  // namespace xq
@@ -1032,7 +1129,7 @@ int xq_dev_set_attn_trace(void *dev_ptr) {
 
 size_t xq_vit_attn_bwd_workspace_bytes(int B, int N, int H) {
     if (B <= 0 || N <= 0 || H <= 0) return 0;
-    return xq::attn_bwd_ws_layout(B, N, H, nullptr, nullptr);
+    return xq::attn_bwd_ws_layout(B, N, H, nullptr, nullptr, nullptr);
 }
 
 int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const float *lse2, void *dqkv, float *g_bias, int B, int N,
@@ -1042,15 +1139,17 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     if (head_dim != AT_D) return XQ_ERR_UNSUPPORTED;
     if (((uintptr_t)qkv & 15) || ((uintptr_t)out & 15) || ((uintptr_t)d_out & 15) || ((uintptr_t)dqkv & 15) || ((uintptr_t)workspace & 255))
         return XQ_ERR_ARG;
-    size_t off_lse, off_delta;
-    if (workspace_bytes < attn_bwd_ws_layout(B, N, H, &off_lse, &off_delta)) return XQ_ERR_WORKSPACE;
+    size_t off_lse, off_delta, off_dst;
+    if (workspace_bytes < attn_bwd_ws_layout(B, N, H, &off_lse, &off_delta, &off_dst)) return XQ_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float *acc = (float *)workspace;
     float *lseP = (float *)((char *)workspace + off_lse);
     float *deltaP = (float *)((char *)workspace + off_delta);
+    float *dsT = (float *)((char *)workspace + off_dst);
     AttnBwdMaps m;
     if (!get_bwd_maps(qkv, d_out, dqkv, acc, B, N, H, m)) return XQ_ERR_UNSUPPORTED;
-    const int nK = (N + AT_BN - 1) / AT_BN;
+    const int nt = attn_bwd_ktail(N);                                     // few trailing keys: CUDA-core kernel, not a key block
+    const int nK = nt ? N / AT_BN : (N + AT_BN - 1) / AT_BN;
     const int Npad = (N + AT_BM - 1) / AT_BM * AT_BM;
     XQ_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * H * N * AT_D * sizeof(float), st));
     if (g_bias) XQ_CUDA_TRY(cudaMemsetAsync(g_bias, 0, (size_t)3 * H * AT_D * sizeof(float), st));
@@ -1071,10 +1170,16 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, g_bias, N, H, nK, Npad,
                                                               scale * 1.4426950408889634f, scale);
     XQ_LAUNCH_CHECK("attn_bwd_kernel");
+    if (nt) {
+        attn_bwd_ktail_kernel<<<(unsigned)(B * H), 256, 0, st>>>((const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)d_out, lseP, deltaP,
+                                                               (__nv_bfloat16 *)dqkv, dsT, g_bias, N, H, N - nt, nt, Npad,
+                                                               scale * 1.4426950408889634f, scale);
+        XQ_LAUNCH_CHECK("attn_bwd_ktail_kernel");
+    }
     {
         if ((long long)B * H > 65535) return XQ_ERR_UNSUPPORTED;
         dim3 grid((unsigned)((N + 31) / 32), (unsigned)(B * H));
-        attn_dq_convert_kernel<<<grid, 256, 0, st>>>(acc, (__nv_bfloat16 *)dqkv, g_bias, N, H, scale);
+        attn_dq_convert_kernel<<<grid, 256, 0, st>>>(acc, (const __nv_bfloat16 *)qkv, dsT, (__nv_bfloat16 *)dqkv, g_bias, N, H, N - nt, nt, scale);
         XQ_LAUNCH_CHECK("attn_dq_convert_kernel");
     }
     return XQ_OK;

@@ -54,6 +54,7 @@ class VectorQuantizer(nn.Module):
             vq_loss, commit_loss = loss2[0], loss2[1]
             self.last_idx = idx
             if ret_usages and self.training:
+                hist = hist.detach()                 # statistics only: no gradient flows through the usage EMA
                 _allreduce_hist_(hist)
                 usage = torch.ops.xqb200.usage_ema_(self.ema_vocab_hit_SV, hist, self._record_hit_dev, margin)[0]
             else:

@@ -656,7 +656,9 @@ def test_vq_custom_ops_compile_fullgraph_and_cuda_graph():
         (oa.sum() * 0.3 + va + ca).backward()
         (ob.sum() * 0.3 + vb + cb).backward()
         assert torch.equal(oa, ob) and torch.equal(qa.last_idx, qb.last_idx) and float(va) == float(vb) and float(ca) == float(cb)
-        assert torch.equal(za.grad, zb.grad) and torch.equal(qa.embedding.weight.grad, qb.embedding.weight.grad)
+        assert torch.equal(za.grad, zb.grad)
+        # the codebook gradient is a float atomic scatter-add: deterministic values, run-to-run summation order
+        assert torch.allclose(qa.embedding.weight.grad, qb.embedding.weight.grad, rtol=1e-5, atol=1e-8)
         assert torch.equal(qa.ema_vocab_hit_SV, qb.ema_vocab_hit_SV) and float(ua[0]) == float(ub[0])
         qa.embedding.weight.grad = None
         qb.embedding.weight.grad = None
@@ -700,5 +702,5 @@ def test_vq_custom_ops_compile_fullgraph_and_cuda_graph():
         (oe.sum() * 0.3 + ve + ce).backward()
         torch.cuda.synchronize()
         assert torch.equal(o, oe) and float(v) == float(ve) and torch.equal(z_static.grad, ze.grad)
-        assert torch.equal(qg.embedding.weight.grad, qe.embedding.weight.grad)
+        assert torch.allclose(qg.embedding.weight.grad, qe.embedding.weight.grad, rtol=1e-5, atol=1e-8)
     assert torch.equal(qg.ema_vocab_hit_SV, qe.ema_vocab_hit_SV)
