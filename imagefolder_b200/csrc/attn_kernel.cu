@@ -898,128 +898,204 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
 }
 
-// delta[bh][n] = sum_d dO * O ; lseP = lse2 re-laid with the row count padded to a multiple of 128 (+inf beyond N, so that
-// padded queries get P = 0) -- both 512-byte-aligned per query block for the bulk copies of attn_bwd_kernel
-__global__ void attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ dout,
-                                     const float *__restrict__ lse2, float *__restrict__ lseP, float *__restrict__ deltaP, int B,
-                                     int N, int H, int Npad) {
-    // 8 threads per (b, n, h) row of 64 values (16 bytes each)
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long rowid = gid >> 3;
-    const int part = (int)(gid & 7);
-    const long long total = (long long)B * H * Npad;
-    if (rowid >= total) return;
-    const int n = (int)(rowid % Npad);
-    const long long bhh = rowid / Npad;
-    const int hh = (int)(bhh % H);
-    const int bb = (int)(bhh / H);
-    float acc = 0.f;
-    if (n < N) {
-        const size_t off = (((size_t)bb * N + n) * H + hh) * AT_D + part * 8;
-        const uint4 a = *reinterpret_cast<const uint4 *>(out + off);
-        const uint4 g = *reinterpret_cast<const uint4 *>(dout + off);
-        const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&a);
-        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&g);
+
+// Backward pre-pass, one launch.  256 threads = 32 rows x 8 lanes (16 B of a 64-wide head row each); a CTA works on 128-row
+// blocks of one (batch, head), four row passes per block with all loads issued up front.
+//   * delta[q] = sum_d dO[q][d] O[q][d]  and the lse copied into the 128-padded layout the main kernel's TMA reads (+inf pads);
+//   * the fp32 dQ accumulator rows are zeroed here (they are this kernel's rows anyway; saves a 400 MB memset node);
+//   * NT > 0 -- the last (N mod 128) keys when they are few (<= AB_KTAIL_MAX; 513 = 4*128 + 1): a whole CTA of attn_bwd_kernel,
+//     five query blocks of full-size MMAs, for one or two key rows is 20 % of that kernel's work at N = 513.  Those keys are
+//     handled here on CUDA cores instead, since dO[q] is in registers already (one more 16 B load for q):
+//         s = c q.k_t ; p = exp2(s - L2[q]) ; dp = dO[q].v_t ; ds = p (dp - delta[q])
+//         dV[t] += p dO[q] ; dK[t] += ds q  (registers; one CTA owns the whole (batch, head), so it also writes the rounded
+//         dK / dV rows of those keys and their share of the qkv-bias gradient) ; ds[q][t] -> dsT.
+//     attn_dq_convert_kernel folds  dQ[q] += sum_t ds[q][t] k_t  in while it converts the accumulator.
+// grid: NT == 0 -> (Npad / 128, B*H);  NT > 0 -> (1, B*H), the CTA loops over the row blocks.
+constexpr int AB_KTAIL_MAX = 4;
+constexpr int AB_PREP_ROWS = 128;
+
+__device__ __forceinline__ void unpack8(const uint4 &w, float (&f)[8]) {
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 x = __bfloat1622float2(a2[e]), y = __bfloat1622float2(g2[e]);
-            acc = fmaf(x.x, y.x, acc);
-            acc = fmaf(x.y, y.y, acc);
-        }
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (part == 0) {
-        deltaP[rowid] = acc;
-        lseP[rowid] = n < N ? lse2[(size_t)bhh * N + n] : CUDART_INF_F;
-    }
+    for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(x[e] << 16); f[2 * e + 1] = __uint_as_float(x[e] & 0xffff0000u); }
 }
 
-// The last (N mod 128) keys when they are few (<= AB_KTAIL_MAX; 513 = 4*128 + 1): a whole CTA of attn_bwd_kernel -- five query
-// blocks of full-size MMAs -- for one or two key rows is 20 % of that kernel's work at N = 513.  Here instead: one CTA per
-// (batch, head), one warp per query (lanes own 2 of the 64 head dims), CUDA cores:
-//     s = c q.k_t ; p = exp2(s - L2[q]) ; dp = dO[q].v_t ; ds = p (dp - delta[q])
-//     dV[t] += p dO[q] ; dK[t] += ds q   (registers, reduced across the 8 warps at the end) ; ds[q][t] -> dsT for the dQ side,
-// which attn_dq_convert_kernel folds in as  dQ[q] += sum_t ds[q][t] k_t  while it converts the accumulator anyway.
-constexpr int AB_KTAIL_MAX = 16;
-
-__global__ void __launch_bounds__(256)
-attn_bwd_ktail_kernel(const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ dout, const float *__restrict__ lseP,
-                      const float *__restrict__ deltaP, __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ dsT,
-                      float *__restrict__ g_bias, int N, int H, int n0, int nt, int Npad, float c, float scale) {
-    __shared__ float2 sk[AB_KTAIL_MAX][32], sv[AB_KTAIL_MAX][32];          // tail key / value rows, [t][lane] = dims 2*lane, 2*lane+1
-    __shared__ float accs[2][AB_KTAIL_MAX][AT_D];                            // dK, dV sums over the CTA
-    const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+template <int NT>
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_prep_kernel(const __nv_bfloat16 *__restrict__ qkv, const __nv_bfloat16 *__restrict__ out, const __nv_bfloat16 *__restrict__ dout,
+                     const float *__restrict__ lse2, float *__restrict__ lseP, float *__restrict__ deltaP, float *__restrict__ dq_acc,
+                     float *__restrict__ dsT, __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias, int N, int H, int Npad,
+                     float c, float scale) {
+    constexpr int NTA = NT > 0 ? NT : 1;
+    __shared__ float red[NT > 0 ? 8 : 1][2][NTA][AT_D];
+    __shared__ __align__(16) float skv[2][NTA][AT_D];
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int lane = threadIdx.x & 31, sub = threadIdx.x & 7, rloc = threadIdx.x >> 3;
+    const int n0 = N - NT;
     const size_t W = (size_t)3 * H * AT_D;
-    const __nv_bfloat16 *base_b = qkv + (size_t)b * N * W;
-    for (int i = threadIdx.x; i < nt * 32; i += 256) {
-        const int t = i >> 5, l = i & 31;
-        const __nv_bfloat16 *kr = base_b + (size_t)(n0 + t) * W + (H + h) * AT_D + 2 * l;
-        sk[t][l] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kr));
-        sv[t][l] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(kr + (size_t)H * AT_D));
+    const __nv_bfloat16 *qb = qkv + (size_t)b * N * W + h * AT_D + sub * 8;
+    const size_t ob = (size_t)b * N * H * AT_D + h * AT_D + sub * 8;
+    float aK[NTA][8], aV[NTA][8];
+    if constexpr (NT > 0) {
+        // tail key / value rows as fp32 in shared memory: [t][d]; 16 threads per t (8 for k, 8 for v), 16 B of bf16 each
+        if (threadIdx.x < NT * 16) {
+            const int t = threadIdx.x >> 4, isv = (threadIdx.x >> 3) & 1;
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4 *>(qb + (size_t)(n0 + t) * W + (size_t)(1 + isv) * H * AT_D), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) skv[isv][t][sub * 8 + e] = f[e];
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) aK[t][e] = aV[t][e] = 0.f;
+        }
+        __syncthreads();
     }
-    for (int i = threadIdx.x; i < 2 * AB_KTAIL_MAX * AT_D; i += 256) (&accs[0][0][0])[i] = 0.f;
-    __syncthreads();
-    float2 aK[AB_KTAIL_MAX], aV[AB_KTAIL_MAX];
+    constexpr int PASSES = AB_PREP_ROWS / 32;
+    // NT > 0: the CTA walks the row blocks of its (batch, head) with the next block's rows in flight (cp.async into a two-stage
+    // shared buffer; every thread reads back only the 16-byte slots it copied itself, so the wait_group is the only sync needed)
+    extern __shared__ uint4 prep_stage[];                                  // [2 stages][3: O, dO, q][PASSES][256 threads]
+    auto prefetch = [&](int blk, int stg) {
 #pragma unroll
-    for (int t = 0; t < AB_KTAIL_MAX; ++t) { aK[t] = make_float2(0.f, 0.f); aV[t] = make_float2(0.f, 0.f); }
-    const float *L = lseP + (size_t)bh * Npad, *Dl = deltaP + (size_t)bh * Npad;
-    for (int q = warp; q < N; q += 8) {
-        const float2 qv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(base_b + (size_t)q * W + h * AT_D + 2 * lane));
-        const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(dout + ((size_t)b * N + q) * H * AT_D + h * AT_D + 2 * lane));
-        const float lq = L[q], dq_ = Dl[q];
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int n = blk * AB_PREP_ROWS + ps * 32 + rloc;
+            const int nc = n < N ? n : N - 1;
+            uint4 *dst = prep_stage + ((size_t)(stg * 3) * PASSES + ps) * 256 + threadIdx.x;
+            cp_async16(dst, out + ob + (size_t)nc * H * AT_D);
+            cp_async16(dst + PASSES * 256, dout + ob + (size_t)nc * H * AT_D);
+            cp_async16(dst + 2 * PASSES * 256, qb + (size_t)nc * W);
+        }
+        cp_async_commit();
+    };
+    if constexpr (NT > 0) prefetch(blockIdx.x, 0);
+    int stg = 0;
+    for (int blk = blockIdx.x; blk * AB_PREP_ROWS < Npad; blk += gridDim.x, stg ^= 1) {
+        uint4 ow[PASSES], gw[PASSES], qw[PASSES];
+        float lq[PASSES];
 #pragma unroll
-        for (int t = 0; t < AB_KTAIL_MAX; ++t) {
-            if (t < nt) {
-                float ps = fmaf(qv.x, sk[t][lane].x, qv.y * sk[t][lane].y);
-                float pd = fmaf(gv.x, sv[t][lane].x, gv.y * sv[t][lane].y);
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int n = blk * AB_PREP_ROWS + ps * 32 + rloc;
+            const int nc = n < N ? n : N - 1;                              // pads: load the last row, results discarded below
+            if constexpr (NT == 0) {
+                ow[ps] = *reinterpret_cast<const uint4 *>(out + ob + (size_t)nc * H * AT_D);
+                gw[ps] = *reinterpret_cast<const uint4 *>(dout + ob + (size_t)nc * H * AT_D);
+            }
+            lq[ps] = lse2[(size_t)bh * N + nc];
+        }
+        if constexpr (NT > 0) {
+            if ((blk + (int)gridDim.x) * AB_PREP_ROWS < Npad) { prefetch(blk + gridDim.x, stg ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+        }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    ps += __shfl_xor_sync(0xffffffffu, ps, o);
-                    pd += __shfl_xor_sync(0xffffffffu, pd, o);
+        for (int ps = 0; ps < PASSES; ++ps) {
+            const int n = blk * AB_PREP_ROWS + ps * 32 + rloc;             // < Npad
+            const bool live = n < N;
+            float ov[8], gv[8];
+            if constexpr (NT > 0) {
+                const uint4 *src = prep_stage + ((size_t)(stg * 3) * PASSES + ps) * 256 + threadIdx.x;
+                ow[ps] = src[0];
+                gw[ps] = src[PASSES * 256];
+                qw[ps] = src[2 * PASSES * 256];
+            }
+            unpack8(ow[ps], ov);
+            unpack8(gw[ps], gv);
+            float dl = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dl = fmaf(ov[e], gv[e], dl);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+            dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+            if (!live) dl = 0.f;
+            if (sub == 0) {
+                deltaP[(size_t)bh * Npad + n] = dl;
+                lseP[(size_t)bh * Npad + n] = live ? lq[ps] : CUDART_INF_F;
+            }
+            if (live) {
+                float4 *z = reinterpret_cast<float4 *>(dq_acc + ((size_t)bh * N + n) * AT_D + sub * 8);
+                z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if constexpr (NT > 0) {
+                float qv[8];
+                unpack8(qw[ps], qv);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    float sx = 0.f, pd = 0.f;
+                    const float4 k0 = *reinterpret_cast<const float4 *>(&skv[0][t][sub * 8]), k1 = *reinterpret_cast<const float4 *>(&skv[0][t][sub * 8 + 4]);
+                    const float4 v0 = *reinterpret_cast<const float4 *>(&skv[1][t][sub * 8]), v1 = *reinterpret_cast<const float4 *>(&skv[1][t][sub * 8 + 4]);
+                    const float kt[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w}, vt[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sx = fmaf(qv[e], kt[e], sx); pd = fmaf(gv[e], vt[e], pd); }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) {
+                        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                        pd += __shfl_xor_sync(0xffffffffu, pd, o);
+                    }
+                    const float p = live ? ex2_approx(fmaf(sx, c, -lq[ps])) : 0.f;
+                    const float ds = p * (pd - dl);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { aV[t][e] = fmaf(p, gv[e], aV[t][e]); aK[t][e] = fmaf(ds, qv[e], aK[t][e]); }
+                    if (sub == 0 && live) dsT[((size_t)bh * N + n) * NT + t] = ds;
                 }
-                const float p = ex2_approx(fmaf(ps, c, -lq));
-                const float ds = p * (pd - dq_);
-                aV[t].x = fmaf(p, gv.x, aV[t].x); aV[t].y = fmaf(p, gv.y, aV[t].y);
-                aK[t].x = fmaf(ds, qv.x, aK[t].x); aK[t].y = fmaf(ds, qv.y, aK[t].y);
-                if (lane == 0) dsT[((size_t)bh * N + q) * nt + t] = ds;
             }
         }
     }
+    if constexpr (NT > 0) {
+        // the 4 row slots of a warp share `sub`: xor-shuffle over 8, 16; then the 8 warps' partials through shared memory (plain
+        // stores: shared-memory float atomics are CAS loops, and 8 warps on the same 128 words serialise badly)
+        const int warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int t = 0; t < AB_KTAIL_MAX; ++t) {
-        if (t < nt) {
-            atomicAdd(&accs[0][t][2 * lane], aK[t].x); atomicAdd(&accs[0][t][2 * lane + 1], aK[t].y);
-            atomicAdd(&accs[1][t][2 * lane], aV[t].x); atomicAdd(&accs[1][t][2 * lane + 1], aV[t].y);
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float a = aK[t][e], v = aV[t][e];
+                a += __shfl_xor_sync(0xffffffffu, a, 8);  v += __shfl_xor_sync(0xffffffffu, v, 8);
+                a += __shfl_xor_sync(0xffffffffu, a, 16); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane < 8) { red[warp][0][t][sub * 8 + e] = a; red[warp][1][t][sub * 8 + e] = v; }
+            }
         }
-    }
-    __syncthreads();
-    // write the dK (scaled) / dV rows of the tail keys into the packed gradient (+ their share of the qkv-bias gradient)
-    for (int i = threadIdx.x; i < 2 * nt * AT_D; i += 256) {
-        const int which = i / (nt * AT_D), r = i - which * nt * AT_D, t = r / AT_D, d = r - t * AT_D;
-        const __nv_bfloat16 val = __float2bfloat16(accs[which][t][d] * (which == 0 ? scale : 1.0f));
-        dqkv[((size_t)b * N + n0 + t) * W + ((which == 0 ? 1 : 2) * H + h) * AT_D + d] = val;
-    }
-    if (g_bias && threadIdx.x < 2 * AT_D) {
-        const int which = threadIdx.x / AT_D, d = threadIdx.x - which * AT_D;
-        float sum = 0.f;
-        for (int t = 0; t < nt; ++t) sum += __bfloat162float(__float2bfloat16(accs[which][t][d] * (which == 0 ? scale : 1.0f)));
-        atomicAdd(g_bias + ((which == 0 ? 1 : 2) * H + h) * AT_D + d, sum);
+        __syncthreads();
+        // dK (scaled) / dV rows of the tail keys -> packed gradient (+ their share of the qkv-bias gradient: sums of the ROUNDED values)
+        if (threadIdx.x < 2 * AT_D) {
+            const int which = threadIdx.x / AT_D, d = threadIdx.x - which * AT_D;
+            float bsum = 0.f;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float sum = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) sum += red[w8][which][t][d];
+                const __nv_bfloat16 val = __float2bfloat16(sum * (which == 0 ? scale : 1.0f));
+                dqkv[((size_t)b * N + n0 + t) * W + (size_t)(1 + which) * H * AT_D + h * AT_D + d] = val;
+                bsum += __bfloat162float(val);
+            }
+            if (g_bias) atomicAdd(g_bias + (size_t)(1 + which) * H * AT_D + h * AT_D + d, bsum);
+        }
     }
 }
 
 // dq_acc fp32 [B*H][N][64] (+ the tail keys' contribution sum_t ds[q][t] k_t) * scale -> dqkv[b][n][0][h][:] bf16 ; optionally the
-// q-part of the qkv-bias gradient (column sums of the rounded values).  grid = (ceil(N / 32), B*H), 256 threads = 32 rows x 8
-// column groups: a block never mixes heads.
-__global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ dsT,
-                                       __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias, int N, int H, int n0, int nt, float scale) {
+// q-part of the qkv-bias gradient (column sums of the rounded values).  grid = (ceil(N / 128), B*H), 256 threads = 32 rows x 8
+// column groups, four row passes with the loads issued up front: a block never mixes heads.
+constexpr int AB_CONV_ROWS = 128;
+
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float *__restrict__ dq_acc, const __nv_bfloat16 *__restrict__ qkv, const float *__restrict__ dsT,
+                       __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias, int N, int H, int n0, int nt, float scale) {
     __shared__ float red[8][AT_D];
     __shared__ float skt[AB_KTAIL_MAX][AT_D];
     const int part = threadIdx.x & 7, rloc = threadIdx.x >> 3;
-    const int bhh = blockIdx.y, n = blockIdx.x * 32 + rloc;
+    const int bhh = blockIdx.y;
     const int hh = bhh % H, bb = bhh / H;
+    constexpr int PASSES = AB_CONV_ROWS / 32;
+    float4 x0[PASSES], x1[PASSES];
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+        const int n = blockIdx.x * AB_CONV_ROWS + ps * 32 + rloc;
+        const size_t rowid = (size_t)bhh * N + (n < N ? n : N - 1);
+        x0[ps] = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
+        x1[ps] = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
+    }
     if (nt > 0) {
         for (int i = threadIdx.x; i < nt * AT_D; i += 256) {
             const int t = i / AT_D, d = i - t * AT_D;
@@ -1030,25 +1106,27 @@ __global__ void attn_dq_convert_kernel(const float *__restrict__ dq_acc, const _
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (n < N) {
-        const size_t rowid = (size_t)bhh * N + n;
-        const float4 x0 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8);
-        const float4 x1 = *reinterpret_cast<const float4 *>(dq_acc + rowid * AT_D + part * 8 + 4);
-        float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        for (int t = 0; t < nt; ++t) {
-            const float ds = dsT[rowid * nt + t];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = fmaf(ds, skt[t][part * 8 + e], x[e]);
+    for (int ps = 0; ps < PASSES; ++ps) {
+        const int n = blockIdx.x * AB_CONV_ROWS + ps * 32 + rloc;
+        if (n < N) {
+            const size_t rowid = (size_t)bhh * N + n;
+            float x[8] = {x0[ps].x, x0[ps].y, x0[ps].z, x0[ps].w, x1[ps].x, x1[ps].y, x1[ps].z, x1[ps].w};
+            for (int t = 0; t < nt; ++t) {
+                const float ds = dsT[rowid * nt + t];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = fmaf(ds, skt[t][part * 8 + e], x[e]);
+            }
+            uint4 o;
+            o.x = pack_bf16(x[0] * scale, x[1] * scale);
+            o.y = pack_bf16(x[2] * scale, x[3] * scale);
+            o.z = pack_bf16(x[4] * scale, x[5] * scale);
+            o.w = pack_bf16(x[6] * scale, x[7] * scale);
+            *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[2 * e] += __uint_as_float(w[e] << 16); v[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u); }
         }
-        uint4 o;
-        o.x = pack_bf16(x[0] * scale, x[1] * scale);
-        o.y = pack_bf16(x[2] * scale, x[3] * scale);
-        o.z = pack_bf16(x[4] * scale, x[5] * scale);
-        o.w = pack_bf16(x[6] * scale, x[7] * scale);
-        *reinterpret_cast<uint4 *>(dqkv + (((size_t)bb * N + n) * 3 * H + hh) * AT_D + part * 8) = o;
-        const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
     }
     if (!g_bias) return;
     // rows of a warp: lanes with equal `part` are 8 apart -> xor-shuffle over 8, 16; then 8 warps through shared memory
@@ -1109,7 +1187,7 @@ static size_t attn_bwd_ws_layout(int B, int N, int H, size_t *off_lse, size_t *o
     const size_t Npad = ((size_t)N + AT_BM - 1) / AT_BM * AT_BM;
     const size_t acc = align_up((size_t)B * H * N * AT_D * sizeof(float), 1024);
     const size_t st = align_up((size_t)B * H * Npad * sizeof(float), 1024);
-    const size_t dst = align_up((size_t)B * H * N * attn_bwd_ktail(N) * sizeof(float), 1024);
+    const size_t dst = align_up((size_t)B * H * N * attn_bwd_ktail(N) * sizeof(float), 1024);    // dsT [B*H][N][nt]
     if (off_lse) *off_lse = acc;
     if (off_delta) *off_delta = acc + st;
     if (off_dst) *off_dst = acc + 2 * st;
@@ -1151,12 +1229,29 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     const int nt = attn_bwd_ktail(N);                                     // few trailing keys: CUDA-core kernel, not a key block
     const int nK = nt ? N / AT_BN : (N + AT_BN - 1) / AT_BN;
     const int Npad = (N + AT_BM - 1) / AT_BM * AT_BM;
-    XQ_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * H * N * AT_D * sizeof(float), st));
+    if ((long long)B * H > 65535) return XQ_ERR_UNSUPPORTED;
     if (g_bias) XQ_CUDA_TRY(cudaMemsetAsync(g_bias, 0, (size_t)3 * H * AT_D * sizeof(float), st));
+    const float c2 = scale * 1.4426950408889634f;
     {
-        const long long threads = (long long)B * H * Npad * 8;
-        attn_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16 *)out, (const __nv_bfloat16 *)d_out,
-                                                                              lse2, lseP, deltaP, B, N, H, Npad);
+        dim3 grid(nt ? 1u : (unsigned)(Npad / AB_PREP_ROWS), (unsigned)(B * H));
+        const __nv_bfloat16 *qp = (const __nv_bfloat16 *)qkv, *op = (const __nv_bfloat16 *)out, *gp = (const __nv_bfloat16 *)d_out;
+        __nv_bfloat16 *dp = (__nv_bfloat16 *)dqkv;
+        constexpr int PS = 2 * 3 * (AB_PREP_ROWS / 32) * 256 * 16;             // the NT > 0 variants' two-stage row buffer
+        static bool prep_attr = false;
+        if (!prep_attr) {
+            XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
+            XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
+            XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
+            XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
+            prep_attr = true;
+        }
+        switch (nt) {
+        case 0: attn_bwd_prep_kernel<0><<<grid, 256, 0, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
+        case 1: attn_bwd_prep_kernel<1><<<grid, 256, PS, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
+        case 2: attn_bwd_prep_kernel<2><<<grid, 256, PS, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
+        case 3: attn_bwd_prep_kernel<3><<<grid, 256, PS, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
+        default: attn_bwd_prep_kernel<4><<<grid, 256, PS, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
+        }
         XQ_LAUNCH_CHECK("attn_bwd_prep_kernel");
     }
     const size_t smem = AttnBwdSmem::BYTES + 1024;
@@ -1168,17 +1263,10 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     const long long ctas = (long long)B * H * nK;
     if (ctas > 0x7fffffffLL) return XQ_ERR_ARG;
     attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, g_bias, N, H, nK, Npad,
-                                                              scale * 1.4426950408889634f, scale);
+                                                              c2, scale);
     XQ_LAUNCH_CHECK("attn_bwd_kernel");
-    if (nt) {
-        attn_bwd_ktail_kernel<<<(unsigned)(B * H), 256, 0, st>>>((const __nv_bfloat16 *)qkv, (const __nv_bfloat16 *)d_out, lseP, deltaP,
-                                                               (__nv_bfloat16 *)dqkv, dsT, g_bias, N, H, N - nt, nt, Npad,
-                                                               scale * 1.4426950408889634f, scale);
-        XQ_LAUNCH_CHECK("attn_bwd_ktail_kernel");
-    }
     {
-        if ((long long)B * H > 65535) return XQ_ERR_UNSUPPORTED;
-        dim3 grid((unsigned)((N + 31) / 32), (unsigned)(B * H));
+        dim3 grid((unsigned)((N + AB_CONV_ROWS - 1) / AB_CONV_ROWS), (unsigned)(B * H));
         attn_dq_convert_kernel<<<grid, 256, 0, st>>>(acc, (const __nv_bfloat16 *)qkv, dsT, (__nv_bfloat16 *)dqkv, g_bias, N, H, N - nt, nt, scale);
         XQ_LAUNCH_CHECK("attn_dq_convert_kernel");
     }

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--lib", type=str, default="", help="alternative libxqb200 build (experiments)")
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--prof", action="store_true", help="per-kernel device times of the backward call")
     a = ap.parse_args()
     if a.lib:
         C.LIB_PATH = os.path.abspath(a.lib)
@@ -104,6 +105,14 @@ def main():
                 o, l = ours_fwd(qkv, H)
                 do = torch.randn(B, N, H * 64, device=dev).to(torch.bfloat16)
                 tb = timeit(lambda: ours_bwd(qkv, o, l, do, H))
+                if a.prof:
+                    from torch.profiler import profile, ProfilerActivity
+                    with profile(activities=[ProfilerActivity.CUDA]) as pr:
+                        for _ in range(5):
+                            ours_bwd(qkv, o, l, do, H)
+                        torch.cuda.synchronize()
+                    for ev in pr.key_averages():
+                        print(f"      {ev.key[:60]:60s} {ev.device_time_total / 5:9.1f} us")
                 qq, kk, vv = (t_.detach().requires_grad_(True) for t_ in (q, k, v))
                 oo = F.scaled_dot_product_attention(qq, kk, vv)
                 gg = do.view(B, N, H, 64).transpose(1, 2)
