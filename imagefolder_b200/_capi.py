@@ -132,14 +132,15 @@ def lib() -> ctypes.CDLL:
 
 
 # --- instrumentation used by bench.py (off by default) ---------------------------------------
-TIMING = None        # dict name -> [(start_event, end_event, algorithmic_bytes), ...] when enabled
+TIMING = None        # dict name -> [(start_event, end_event, algorithmic_bytes, tensor_flops), ...] when enabled
 LAUNCHES = [0]       # number of libxqb200 kernels launched (counted per C call)
 
 
-def call(name: str, n_kernels: int, fn, *args, nbytes: int = 0) -> None:
+def call(name: str, n_kernels: int, fn, *args, nbytes: int = 0, nflops: float = 0.0) -> None:
     """invoke a C-ABI entry point, map its return code, count its kernel launches and (when
     TIMING is enabled) bracket it with CUDA events on the current stream.  `nbytes` = the call's algorithmic
-    HBM bytes (what it must read + write once), recorded for bench.py's per-kernel roofline table."""
+    HBM bytes (what it must read + write once), `nflops` = its tensor-core FLOPs (contractions only), recorded for
+    bench.py's per-kernel roofline table."""
     LAUNCHES[0] += n_kernels
     if TIMING is None:
         check(fn(*args), name)
@@ -148,7 +149,7 @@ def call(name: str, n_kernels: int, fn, *args, nbytes: int = 0) -> None:
     s.record()
     rc = fn(*args)
     e.record()
-    TIMING.setdefault(name, []).append((s, e, nbytes))
+    TIMING.setdefault(name, []).append((s, e, nbytes, nflops))
     check(rc, name)
 
 

@@ -137,7 +137,8 @@ def attn_tc_forward(qkv, num_heads: int):
     lse2 = torch.empty(B, num_heads, N, dtype=torch.float32, device=qkv.device)
     L = _lib()
     _call("xq_vit_attn_fwd", 1, L.xq_vit_attn_fwd, _ptr(qkv), _ptr(out), _ptr(lse2), B, N, num_heads, 64, 0.125,
-          _stream(qkv.device), nbytes=qkv.numel() * 2 + out.numel() * 2 + lse2.numel() * 4)
+          _stream(qkv.device), nbytes=qkv.numel() * 2 + out.numel() * 2 + lse2.numel() * 4,
+          nflops=4.0 * B * num_heads * N * N * 64)
     return out, lse2
 
 
@@ -161,7 +162,8 @@ def attn_tc_backward(qkv, out, lse2, g, num_heads: int, want_bias_grad: bool = F
         ws = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
         _ATTN_WS[key] = ws
     _call("xq_vit_attn_bwd", 3, L.xq_vit_attn_bwd, _ptr(qkv), _ptr(out), _ptr(g), _ptr(lse2), _ptr(dqkv), _ptr(db), B, N, num_heads,
-          64, 0.125, _ptr(ws), ws.numel(), _stream(qkv.device), nbytes=qkv.numel() * 4 + out.numel() * 4 + lse2.numel() * 4)
+          64, 0.125, _ptr(ws), ws.numel(), _stream(qkv.device), nbytes=qkv.numel() * 4 + out.numel() * 4 + lse2.numel() * 4,
+          nflops=10.0 * B * num_heads * N * N * 64)
     return (dqkv, db) if want_bias_grad else dqkv
 
 

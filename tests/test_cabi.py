@@ -83,13 +83,21 @@ def test_bench_helpers_are_total():
     spec = importlib.util.spec_from_file_location("_bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
-    rows = [{"entry": "xq_vit_residual_ln_bwd", "calls_per_step": 50.0, "ms_per_step": 16.7, "ms_per_call": 0.334, "alg_GBps": 5350.0},
-            {"entry": "xq_vq_forward", "calls_per_step": 1.0, "ms_per_step": 0.2, "ms_per_call": 0.2, "alg_GBps": None}]
-    r = b.top_kernel_roofline(rows, 6385.8, 211.0, {"xq_vit_residual_ln_bwd": 1.788e9})
+    rows = [{"entry": "xq_vit_residual_ln_bwd", "calls_per_step": 50.0, "ms_per_step": 16.7, "ms_per_call": 0.334, "alg_GBps": 5350.0,
+             "alg_TFps": None, "alg_bytes_per_call": 1.787e9, "alg_flops_per_call": 0.0},
+            {"entry": "xq_vq_forward", "calls_per_step": 1.0, "ms_per_step": 0.2, "ms_per_call": 0.2, "alg_GBps": None,
+             "alg_TFps": None, "alg_bytes_per_call": 0, "alg_flops_per_call": 0.0}]
+    r = b.top_kernel_roofline(rows, 6385.8, 1678.2, 211.0, {"xq_vit_residual_ln_bwd": 1.788e9})
     assert r["kernel"] == "xq_vit_residual_ln_bwd" and r["bound"] == "hbm" and abs(r["frac"] - 5350.0 / 6385.8) < 1e-12
     assert r["traffic"] == 1.788e9 and abs(r["share_of_step"] - 16.7 / 211.0) < 1e-12
-    assert b.top_kernel_roofline([], 6385.8, 1.0) is None
-    assert b.top_kernel_roofline(rows[1:], 6385.8, 1.0) is None
+    # an entry with tensor FLOPs is reported against the roof it sits closer to
+    attn = {"entry": "xq_vit_attn_bwd", "calls_per_step": 24.0, "ms_per_step": 32.0, "ms_per_call": 1.33, "alg_GBps": 1100.0,
+            "alg_TFps": 390.0, "alg_bytes_per_call": 1.46e9, "alg_flops_per_call": 5.17e11}
+    r = b.top_kernel_roofline(rows + [attn], 6385.8, 1678.2, 211.0)
+    assert r["kernel"] == "xq_vit_attn_bwd" and r["bound"] == "tensor" and abs(r["frac"] - 390.0 / 1678.2) < 1e-12
+    assert r["traffic"] is None and abs(r["hbm_frac"] - 1100.0 / 6385.8) < 1e-12
+    assert b.top_kernel_roofline([], 6385.8, 1678.2, 1.0) is None
+    assert b.top_kernel_roofline(rows[1:], 6385.8, 1678.2, 1.0) is None
     assert "error" in b._safe(lambda: 1 / 0) and b._safe(lambda: 3) == 3
     hbm, tf, src = b.peaks()
     assert hbm > 1000 and tf > 100 and src in ("measured", "fallback")
