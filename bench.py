@@ -146,11 +146,15 @@ def _safe(fn):
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source).  Every kernel bench.py times sits inside a long training step, so the tensor
+    roof is the SUSTAINED cuBLAS figure of MEASURED_PEAKS.json (the burst one is for a kernel timed alone)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        if "bf16_tflops_sustained" in d:
+            return d.get("hbm_gbs", 6650.0), d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -389,9 +393,6 @@ def run_ours(a):
     # under a loaded GPU was measured to stall 150-700 ms here)
     copy_stream = torch.cuda.Stream(device=dev)
     loss_pinned = torch.empty(a.steps, dtype=torch.float32).pin_memory()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
     # every step: H2D of ITS inputs from pinned memory (prefetched on a copy stream while the previous step computes,
     # as a data loader does) and a D2H read of ITS loss (async into pinned memory; synchronised before the clock stops)
 
@@ -402,6 +403,16 @@ def run_ours(a):
             ev.record(copy_stream)
         return xb, ev
 
+    # one untimed pass through this path (the first use of the copy stream / the first pinned->device DMA of a process was
+    # measured at ~100 ms on a 2-GPU box; it is a warm-up cost like the W compute steps above)
+    xw, evw = prefetch()
+    torch.cuda.current_stream().wait_event(evw)
+    xw.record_stream(torch.cuda.current_stream())
+    loss_pinned[0:1].copy_(step(xw).detach().float().reshape(1), non_blocking=True)
+    del xw
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
     nxt = prefetch()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     for i in range(a.steps):
