@@ -494,12 +494,60 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                  : "memory");
 }
 
+// dV / dK epilogue of one item: the thread's accumulator row (64 fp32 from TMEM, already in o[]) * mul -> bf16 -> 128 contiguous
+// bytes of the packed gradient, and the column sums of the ROUNDED values of the warp's 32 rows -> qkv-bias gradient.  The sums
+// are a transpose-reduce butterfly over the warp (lane = row): 62 shuffles, after which lane l holds columns c0 and c0 + 1,
+// c0 = 32 b4 + 16 b3 + 8 b2 + 4 b1 + 2 b0 (bits of l) -> 2 atomics per lane.  The first butterfly step is fused with the rounding
+// (column chunk j and chunk j + 32 together) so that at most ~64 values are live.  Rows beyond N hold zeros (masked keys) and
+// are not stored.
+__device__ __forceinline__ void bwd_store_rows(uint32_t (&o)[64], float mul, __nv_bfloat16 *__restrict__ dst_row, bool row_ok,
+                                               float *__restrict__ g_bias_cols, int lane) {
+    float a[32], b[16], c[8], d[4];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t wl[4], wh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            wl[e] = pack_bf16(__uint_as_float(o[c8 * 8 + 2 * e]) * mul, __uint_as_float(o[c8 * 8 + 2 * e + 1]) * mul);
+            wh[e] = pack_bf16(__uint_as_float(o[32 + c8 * 8 + 2 * e]) * mul, __uint_as_float(o[32 + c8 * 8 + 2 * e + 1]) * mul);
+        }
+        if (row_ok) {
+            *reinterpret_cast<uint4 *>(dst_row + c8 * 8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            *reinterpret_cast<uint4 *>(dst_row + 32 + c8 * 8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        }
+        if (g_bias_cols) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float l0 = __uint_as_float(wl[e] << 16), l1 = __uint_as_float(wl[e] & 0xffff0000u);
+                const float h0 = __uint_as_float(wh[e] << 16), h1 = __uint_as_float(wh[e] & 0xffff0000u);
+                a[c8 * 8 + 2 * e] = (b4 ? h0 : l0) + __shfl_xor_sync(0xffffffffu, b4 ? l0 : h0, 16);
+                a[c8 * 8 + 2 * e + 1] = (b4 ? h1 : l1) + __shfl_xor_sync(0xffffffffu, b4 ? l1 : h1, 16);
+            }
+        }
+    }
+    if (g_bias_cols) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = (b3 ? a[16 + j] : a[j]) + __shfl_xor_sync(0xffffffffu, b3 ? a[j] : a[16 + j], 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = (b2 ? b[8 + j] : b[j]) + __shfl_xor_sync(0xffffffffu, b2 ? b[j] : b[8 + j], 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = (b1 ? c[4 + j] : c[j]) + __shfl_xor_sync(0xffffffffu, b1 ? c[j] : c[4 + j], 2);
+        const float s0 = (b0 ? d[2] : d[0]) + __shfl_xor_sync(0xffffffffu, b0 ? d[0] : d[2], 1);
+        const float s1 = (b0 ? d[3] : d[1]) + __shfl_xor_sync(0xffffffffu, b0 ? d[1] : d[3], 1);
+        const int c0 = (b4 ? 32 : 0) + (b3 ? 16 : 0) + (b2 ? 8 : 0) + (b1 ? 4 : 0) + (b0 ? 2 : 0);
+        atomicAdd(g_bias_cols + c0, s0);
+        atomicAdd(g_bias_cols + c0 + 1, s1);
+    }
+}
+
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmDQ,
-                const float *__restrict__ lseP, const float *__restrict__ deltaP, float *__restrict__ g_bias, int N, int H, int nK,
-                int Npad, float c, float scale) {
+                const __grid_constant__ CUtensorMap tmDQ, const float *__restrict__ lseP, const float *__restrict__ deltaP,
+                __nv_bfloat16 *__restrict__ dqkv, float *__restrict__ g_bias, int N, int H, int nK, int Npad, int n_items, float c,
+                float scale) {
     extern __shared__ uint8_t smem_raw[];
+    XQ_TR(threadIdx.x == 0, 16 * 30 + 4);
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
     uint64_t *kv_full = bars + 0;
@@ -514,17 +562,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint64_t *ds_full = bars + 13;    // dS_i in TMEM and smem              (4 warps of wgD)
     uint64_t *dq_full = bars + 14;    // dQ_i partial in TMEM               (MMA commit)
     uint64_t *dq_free = bars + 15;    // dQ_i drained                       (4 warps of wgQ)
-    uint64_t *dkv_done = bars + 16;
-    uint32_t *tmem_holder = (uint32_t *)(bars + 17);
+    uint64_t *dkv_done = bars + 16;   // dV / dK of the item complete          (MMA commit)
+    uint64_t *kv_free = bars + 17;    // last MMA reading K / V of the item retired (MMA commit): the tiles may be reloaded
+    uint64_t *dkv_free = bars + 18;   // dV / dK of the item in registers      (4 warps of wgE0 + 4 of wgD0)
+    uint32_t *tmem_holder = (uint32_t *)(bars + 19);
     float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [AB_QS][128]
     float *s_delta = s_lse + AB_QS * 128;                        // [AB_QS][128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bh = blockIdx.x / nK, jb = blockIdx.x - bh * nK;
-    const int b = bh / H, h = bh - b * H;
-    const int k0 = jb * AT_BN;
+    // PERSISTENT: the CTA walks items (batch*head, key block) blockIdx.x, + gridDim.x, ...; every pipeline below keeps running
+    // across item boundaries on one global query-block counter g (barrier parities are functions of g, or of the item count n
+    // for the per-item barriers), so that the dQ drain and the dK / dV epilogue of item n overlap the first blocks of item n+1
+    // and no CTA launch / barrier init / TMEM allocation sits between items.
+    struct Item { int bh, b, h, k0, colQ, colK, colV; };
+    auto item_at = [&](int it) {
+        Item t;
+        t.bh = it / nK;
+        t.b = t.bh / H; t.h = t.bh - t.b * H;
+        t.k0 = (it - t.bh * nK) * AT_BN;
+        t.colQ = t.h * AT_D; t.colK = (H + t.h) * AT_D; t.colV = (2 * H + t.h) * AT_D;
+        return t;
+    };
     const int nQ = Npad / AT_BM;
-    const int colQ = h * AT_D, colK = (H + h) * AT_D, colV = (2 * H + h) * AT_D;
 
     if (tid == 0) {
         mbar_init(kv_full, 1);
@@ -534,6 +593,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_init(dv_done, 1); mbar_init(dp_full, 1);
         mbar_init(ds_full, 8); mbar_init(dq_full, 1);
         mbar_init(dq_free, 4); mbar_init(dkv_done, 1);
+        mbar_init(kv_free, 1); mbar_init(dkv_free, 8);
         mbar_fence_init();
     }
     if (warp == 17) tmem_alloc<512>(tmem_holder);
@@ -557,22 +617,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (elect_one()) {
                 tma_prefetch_desc(&tmQKV);
                 tma_prefetch_desc(&tmDO);
-                mbar_expect_tx(kv_full, 2 * AT_TILE);
-                tma_load_3d(base + AttnBwdSmem::K, &tmQKV, colK, k0, b, kv_full);
-                tma_load_3d(base + AttnBwdSmem::V, &tmQKV, colV, k0, b, kv_full);
             }
             __syncwarp();
-            for (int i = 0; i < nQ; ++i) {
-                const int st = i % AB_QS;
-                mbar_wait(&q_empty[st], ((i / AB_QS) & 1) ^ 1);
+            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+                const Item T = item_at(it);
+                if (n > 0) mbar_wait(kv_free, (n - 1) & 1);          // every MMA that reads the previous item's K / V has retired
                 if (elect_one()) {
-                    mbar_expect_tx(&q_full[st], 2 * AT_TILE + 1024);
-                    tma_load_3d(base + AttnBwdSmem::Q + st * AT_TILE, &tmQKV, colQ, i * AT_BM, b, &q_full[st]);
-                    tma_load_3d(base + AttnBwdSmem::DO + st * AT_TILE, &tmDO, h * AT_D, i * AT_BM, b, &q_full[st]);
-                    bulk_load_1d(s_lse + st * 128, lseP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
-                    bulk_load_1d(s_delta + st * 128, deltaP + (size_t)bh * Npad + i * AT_BM, 512, &q_full[st]);
+                    mbar_expect_tx(kv_full, 2 * AT_TILE);
+                    tma_load_3d(base + AttnBwdSmem::K, &tmQKV, T.colK, T.k0, T.b, kv_full);
+                    tma_load_3d(base + AttnBwdSmem::V, &tmQKV, T.colV, T.k0, T.b, kv_full);
                 }
                 __syncwarp();
+                for (int i = 0; i < nQ; ++i) {
+                    const int g = n * nQ + i, st = g % AB_QS;
+                    mbar_wait(&q_empty[st], ((g / AB_QS) & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&q_full[st], 2 * AT_TILE + 1024);
+                        tma_load_3d(base + AttnBwdSmem::Q + st * AT_TILE, &tmQKV, T.colQ, i * AT_BM, T.b, &q_full[st]);
+                        tma_load_3d(base + AttnBwdSmem::DO + st * AT_TILE, &tmDO, T.h * AT_D, i * AT_BM, T.b, &q_full[st]);
+                        bulk_load_1d(s_lse + st * 128, lseP + (size_t)T.bh * Npad + i * AT_BM, 512, &q_full[st]);
+                        bulk_load_1d(s_delta + st * 128, deltaP + (size_t)T.bh * Npad + i * AT_BM, 512, &q_full[st]);
+                    }
+                    __syncwarp();
+                }
             }
         } else if (warp == 17) {
             // ===== MMA issuer (whole warp runs the control flow, one elected lane issues: see elect_one) =====
@@ -587,9 +654,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             const uint64_t dsd = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
             const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
             const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
-            auto issue_s = [&](int i) {
+            auto issue_s = [&](int i, int g) {
                 if (elect_one()) {
-                    const uint64_t qdk = desc_adv(qd_k0, (i % AB_QS) * AT_TILE);
+                    const uint64_t qdk = desc_adv(qd_k0, (g % AB_QS) * AT_TILE);
                     const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
                     for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(kd_k, k * 32), desc_adv(qdk, k * 32), id, k > 0);
@@ -597,9 +664,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 __syncwarp();
             };
-            auto issue_dp = [&](int i) {
+            auto issue_dp = [&](int i, int g) {
                 if (elect_one()) {
-                    const uint64_t ddk = desc_adv(dd_k0, (i % AB_QS) * AT_TILE);
+                    const uint64_t ddk = desc_adv(dd_k0, (g % AB_QS) * AT_TILE);
                     const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
                     for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_adv(vd_k, k * 32), desc_adv(ddk, k * 32), id, k > 0);
@@ -607,67 +674,77 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 __syncwarp();
             };
-            mbar_wait(kv_full, 0);
-            mbar_wait(&q_full[0], 0);
-            tc_fence_after();
-            issue_s(0);
-            issue_dp(0);
-            for (int i = 0; i < nQ; ++i) {
-                const int st = i % AB_QS;
-                const int ks = nq_of(i) / 16;
-                const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
-                const bool more = i + 1 < nQ;
-                if (more) {
-                    mbar_wait(s_free, i & 1);
-                    mbar_wait(&q_full[(i + 1) % AB_QS], ((i + 1) / AB_QS) & 1);
+            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+                const int g0 = n * nQ;
+                mbar_wait(kv_full, n & 1);
+                mbar_wait(&q_full[g0 % AB_QS], (g0 / AB_QS) & 1);
+                if (g0 > 0) mbar_wait(s_free, (g0 - 1) & 1);          // S^T of the previous item's last block has left TMEM
+                tc_fence_after();
+                issue_s(0, g0);
+                issue_dp(0, g0);          // dP^T columns: in program order behind the previous item's last dK MMA (their last reader)
+                for (int i = 0; i < nQ; ++i) {
+                    const int g = g0 + i, st = g % AB_QS;
+                    const int ks = nq_of(i) / 16;
+                    const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
+                    const bool more = i + 1 < nQ;
+                    if (more) {
+                        mbar_wait(s_free, g & 1);
+                        mbar_wait(&q_full[(g + 1) % AB_QS], ((g + 1) / AB_QS) & 1);
+                        tc_fence_after();
+                        issue_s(i + 1, g + 1);
+                    }
+                    mbar_wait(p_full, g & 1);
+                    XQ_TR(g < 30 && lane == 0, 16 * g + 0);
+                    if (i == 0 && n > 0) mbar_wait(dkv_free, (n - 1) & 1);   // the previous item's dV / dK have left TMEM
                     tc_fence_after();
-                    issue_s(i + 1);
-                }
-                mbar_wait(p_full, i & 1);
-                XQ_TR(i < 30 && lane == 0, 16 * i + 0);
-                tc_fence_after();
-                if (elect_one()) {
-                    for (int k = 0; k < ks; ++k)      // dV += P^T dO : 16 queries per k-step
-                        umma_ts(tDV, tP + k * 8, desc_adv(dd_mn, k * 2048), id_acc, (uint32_t)(i | k));   // P^T: 8 columns per k-step, contiguous
-                    umma_commit(dv_done);
-                }
-                __syncwarp();
-                mbar_wait(ds_full, i & 1);
-                XQ_TR(i < 30 && lane == 0, 16 * i + 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    for (int k = 0; k < ks; ++k)      // dK += dS^T Q : each query half keeps its dS^T (bf16) over the start of its own dP^T columns
-                        umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_adv(qd_mn, k * 2048), id_acc, (uint32_t)(i | k));
-                    umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
-                }
-                __syncwarp();
-                if (more) issue_dp(i + 1);
-                if (i > 0) { mbar_wait(dq_free, (i - 1) & 1); tc_fence_after(); }
-                if (elect_one()) {
-                    const uint64_t dsi = desc_adv(dsd, (i & 1) * 2 * AT_TILE);
+                    if (elect_one()) {
+                        for (int k = 0; k < ks; ++k)      // dV += P^T dO : 16 queries per k-step
+                            umma_ts(tDV, tP + k * 8, desc_adv(dd_mn, k * 2048), id_acc, (uint32_t)(i | k));   // P^T: 8 columns per k-step, contiguous
+                        umma_commit(dv_done);
+                    }
+                    __syncwarp();
+                    mbar_wait(ds_full, g & 1);
+                    XQ_TR(g < 30 && lane == 0, 16 * g + 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        for (int k = 0; k < ks; ++k)      // dK += dS^T Q : each query half keeps its dS^T (bf16) over the start of its own dP^T columns
+                            umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_adv(qd_mn, k * 2048), id_acc, (uint32_t)(i | k));
+                        umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
+                    }
+                    __syncwarp();
+                    if (more) issue_dp(i + 1, g + 1);
+                    if (g > 0) { mbar_wait(dq_free, (g - 1) & 1); tc_fence_after(); }
+                    if (elect_one()) {
+                        const uint64_t dsi = desc_adv(dsd, (g & 1) * 2 * AT_TILE);
 #pragma unroll
-                    for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
-                        umma_ss(tDQ, desc_adv(dsi, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
-                    umma_commit(dq_full);
+                        for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
+                            umma_ss(tDQ, desc_adv(dsi, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
+                        umma_commit(dq_full);
+                    }
+                    __syncwarp();
+                    XQ_TR(g < 30 && lane == 0, 16 * g + 2);
+                }
+                if (elect_one()) {
+                    umma_commit(dkv_done);
+                    umma_commit(kv_free);
                 }
                 __syncwarp();
-                XQ_TR(i < 30 && lane == 0, 16 * i + 2);
             }
-            if (elect_one()) umma_commit(dkv_done);
-            __syncwarp();
         }
     } else if (warp < 8) {
         reg_inc<88>();
         // ===== wgE (warps 0-7): P^T = exp2(S^T c - L2[q]); thread = (key row, query half hf): the MUFU warpgroups =====
         const int hf = warp >> 2;
-        const bool key_ok = k0 + krow < N;
-        const bool keys_full = k0 + AT_BN <= N;      // warp-uniform: no key of this block needs masking
+        for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+        const Item T = item_at(it);
+        const bool key_ok = T.k0 + krow < N;
+        const bool keys_full = T.k0 + AT_BN <= N;    // warp-uniform: no key of this block needs masking
         for (int i = 0; i < nQ; ++i) {
-            const int st = i % AB_QS;
+            const int gq = n * nQ + i, st = gq % AB_QS;
             const int nqr = nq_of(i);
-            mbar_wait(&q_full[st], (i / AB_QS) & 1);                // statistics of this query block are in smem
-            mbar_wait(s_full, i & 1);
-            XQ_TR(i < 30 && warp == 0 && lane == 0, 16 * i + 4);
+            mbar_wait(&q_full[st], (gq / AB_QS) & 1);               // statistics of this query block are in smem
+            mbar_wait(s_full, gq & 1);
+            XQ_TR(gq < 30 && warp == 0 && lane == 0, 16 * gq + 4);
             tc_fence_after();
             const uint32_t l4 = smem_u32(s_lse + st * 128 + hf * 64);
             const bool fast = keys_full && nqr == AT_BM;
@@ -697,9 +774,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     pk[2 * g] = pack_bf16(p0, p1);
                     pk[2 * g + 1] = pack_bf16(p2, p3);
                 }
-                if (ch == 0 && i > 0) {                             // the P buffer is free: dV_{i-1} retired and wgD holds P_{i-1}
-                    mbar_wait(dv_done, (i - 1) & 1);
-                    mbar_wait(p_read, (i - 1) & 1);
+                if (ch == 0 && gq > 0) {                            // the P buffer is free: dV_{g-1} retired and wgD holds P_{g-1}
+                    mbar_wait(dv_done, (gq - 1) & 1);
+                    mbar_wait(p_read, (gq - 1) & 1);
                     tc_fence_after();
                 }
                 tmem_st16(tP + lane_addr + hf * 32 + ch * 16, pk);
@@ -708,46 +785,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            XQ_TR(i < 30 && warp == 0 && lane == 0, 16 * i + 5);
+            XQ_TR(gq < 30 && warp == 0 && lane == 0, 16 * gq + 5);
         }
         if (hf == 0) {
-        // ---- epilogue: dV -> bf16 -> smem -> TMA store
-        mbar_wait(dkv_done, 0);
+        // ---- epilogue of the item: dV (TMEM) -> registers (the accumulator is then free for the next item) -> bf16 -> global
+        XQ_TR(n == 0 && tid == 0, 16 * 30 + 5);
+        mbar_wait(dkv_done, n & 1);
         tc_fence_after();
-        {
-            uint8_t *so = base + AttnBwdSmem::Q;                     // every Q stage is dead
-            const uint32_t so_a = smem_u32(so);
+        XQ_TR(n == 0 && tid == 0, 16 * 30 + 6);
+        uint32_t o[64];
 #pragma unroll
-            for (int c0 = 0; c0 < AT_D; c0 += 16) {
-                uint32_t o[16];
-                tmem_ld16(tDV + lane_addr + c0, o);
-                tmem_wait_ld();
-                uint4 v0, v1;
-                v0.x = pack_bf16(__uint_as_float(o[0]), __uint_as_float(o[1]));
-                v0.y = pack_bf16(__uint_as_float(o[2]), __uint_as_float(o[3]));
-                v0.z = pack_bf16(__uint_as_float(o[4]), __uint_as_float(o[5]));
-                v0.w = pack_bf16(__uint_as_float(o[6]), __uint_as_float(o[7]));
-                v1.x = pack_bf16(__uint_as_float(o[8]), __uint_as_float(o[9]));
-                v1.y = pack_bf16(__uint_as_float(o[10]), __uint_as_float(o[11]));
-                v1.z = pack_bf16(__uint_as_float(o[12]), __uint_as_float(o[13]));
-                v1.w = pack_bf16(__uint_as_float(o[14]), __uint_as_float(o[15]));
-                sts128(so_a + rowtile_unit(krow, c0 / 8), v0);
-                sts128(so_a + rowtile_unit(krow, c0 / 8 + 1), v1);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            named_bar_sync(2, 128);
-            if (tid == 0) {
-                tma_store_3d(&tmDQKV, so, colV, k0, b);
-                bulk_commit();
-            }
-            if (g_bias && tid < AT_D) {               // qkv-bias gradient: column sums of the (bf16-rounded) tile, valid key rows only
-                const int rows = min(AT_BN, N - k0);
-                float acc = 0.f;
-                for (int r = 0; r < rows; ++r) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(so + rowtile_off_bf16(r, tid)));
-                atomicAdd(g_bias + colV + tid, acc);
-            }
-            if (tid == 0) bulk_wait<0>();
+        for (int c0 = 0; c0 < AT_D; c0 += 16) tmem_ld16(tDV + lane_addr + c0, *reinterpret_cast<uint32_t (*)[16]>(&o[c0]));
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_free);
+        bwd_store_rows(o, 1.0f, dqkv + ((size_t)T.b * N + T.k0 + krow) * (size_t)(3 * H * AT_D) + T.colV, key_ok,
+                       g_bias ? g_bias + T.colV : nullptr, lane);
+        XQ_TR(n == 0 && tid == 0, 16 * 30 + 8);
         }
         }
     } else if (warp < 16) {
@@ -755,13 +810,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // ===== wgD (warps 8-15): dS^T = P^T o (dP^T - delta[q]); thread = (key row, query half hf): the FMA warpgroups =====
         const int hf = (warp - 8) >> 2;
         const uint32_t dsrow0 = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
+        for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+        const Item T = item_at(it);
         for (int i = 0; i < nQ; ++i) {
-            const uint32_t dsrow = dsrow0 + (i & 1) * 2 * AT_TILE;     // double-buffered dS operand of the dQ MMA
-            const int st = i % AB_QS;
+            const int gq = n * nQ + i, st = gq % AB_QS;
+            const uint32_t dsrow = dsrow0 + (gq & 1) * 2 * AT_TILE;    // double-buffered dS operand of the dQ MMA
             const int nqr = nq_of(i);
-            mbar_wait(&q_full[st], (i / AB_QS) & 1);
-            mbar_wait(p_full, i & 1);
-            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 8);
+            mbar_wait(&q_full[st], (gq / AB_QS) & 1);
+            mbar_wait(p_full, gq & 1);
+            XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 8);
             tc_fence_after();
             uint32_t pk[32];                                          // this half of P^T as written by wgE: 2 bf16 per word
             tmem_ld32(tP + lane_addr + hf * 32, pk);
@@ -769,8 +826,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_read);
-            mbar_wait(dp_full, i & 1);
-            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 9);
+            mbar_wait(dp_full, gq & 1);
+            XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 9);
             // this dS buffer was last read by the dQ_{i-2} MMA (long retired: dq_full(i-2) completed before dq_free(i-2), which the
             // MMA warp waited for before issuing dQ_{i-1}, which precedes dP^T_i in its program order)
             tc_fence_after();
@@ -805,54 +862,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 // ... and dS for the dQ MMA (smem, MN-major: row = key, this half's 64 queries along the row)
                 sts128(dsrow + rowtile_unit(krow, ch * 2), make_uint4(o8[0], o8[1], o8[2], o8[3]));
                 sts128(dsrow + rowtile_unit(krow, ch * 2 + 1), make_uint4(o8[4], o8[5], o8[6], o8[7]));
-                XQ_TR(i < 30 && warp == 8 && lane == 0 && ch < 3, 16 * i + 13 + ch);
+                XQ_TR(gq < 30 && warp == 8 && lane == 0 && ch < 3, 16 * gq + 13 + ch);
             }
-            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 11);
+            XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 11);
             fence_async_smem();
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
-            XQ_TR(i < 30 && warp == 8 && lane == 0, 16 * i + 10);
+            XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 10);
         }
         if (hf == 0) {
-        // ---- epilogue: dK * scale -> bf16 -> smem -> TMA store
-        mbar_wait(dkv_done, 0);
+        // ---- epilogue of the item: dK (TMEM) -> registers -> * scale -> bf16 -> global
+        mbar_wait(dkv_done, n & 1);
         tc_fence_after();
-        {
-            uint8_t *so = base + AttnBwdSmem::Q + AT_TILE;
-            const uint32_t so_a = smem_u32(so);
+        uint32_t o[64];
 #pragma unroll
-            for (int c0 = 0; c0 < AT_D; c0 += 16) {
-                uint32_t o[16];
-                tmem_ld16(tDK + lane_addr + c0, o);
-                tmem_wait_ld();
-                uint4 v0, v1;
-                v0.x = pack_bf16(__uint_as_float(o[0]) * scale, __uint_as_float(o[1]) * scale);
-                v0.y = pack_bf16(__uint_as_float(o[2]) * scale, __uint_as_float(o[3]) * scale);
-                v0.z = pack_bf16(__uint_as_float(o[4]) * scale, __uint_as_float(o[5]) * scale);
-                v0.w = pack_bf16(__uint_as_float(o[6]) * scale, __uint_as_float(o[7]) * scale);
-                v1.x = pack_bf16(__uint_as_float(o[8]) * scale, __uint_as_float(o[9]) * scale);
-                v1.y = pack_bf16(__uint_as_float(o[10]) * scale, __uint_as_float(o[11]) * scale);
-                v1.z = pack_bf16(__uint_as_float(o[12]) * scale, __uint_as_float(o[13]) * scale);
-                v1.w = pack_bf16(__uint_as_float(o[14]) * scale, __uint_as_float(o[15]) * scale);
-                sts128(so_a + rowtile_unit(krow, c0 / 8), v0);
-                sts128(so_a + rowtile_unit(krow, c0 / 8 + 1), v1);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            named_bar_sync(3, 128);
-            if (tid == 256) {
-                tma_store_3d(&tmDQKV, so, colK, k0, b);
-                bulk_commit();
-            }
-            if (g_bias && tid - 256 < AT_D) {
-                const int cidx = tid - 256, rows = min(AT_BN, N - k0);
-                float acc = 0.f;
-                for (int r = 0; r < rows; ++r) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(so + rowtile_off_bf16(r, cidx)));
-                atomicAdd(g_bias + colK + cidx, acc);
-            }
-            if (tid == 256) bulk_wait<0>();
+        for (int c0 = 0; c0 < AT_D; c0 += 16) tmem_ld16(tDK + lane_addr + c0, *reinterpret_cast<uint32_t (*)[16]>(&o[c0]));
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_free);
+        bwd_store_rows(o, scale, dqkv + ((size_t)T.b * N + T.k0 + krow) * (size_t)(3 * H * AT_D) + T.colK, T.k0 + krow < N,
+                       g_bias ? g_bias + T.colK : nullptr, lane);
         }
         }
     } else {
@@ -860,8 +892,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         // ===== wgQ (warps 20-23): dQ_i partial (TMEM lanes = queries) -> fp32 smem row tiles -> TMA reduce-add =====
         const uint32_t stg = smem_u32(base + AttnBwdSmem::DQ);
         const bool issuer = tid == 20 * 32;
+        for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+        const int bh = it / nK;
         for (int i = 0; i < nQ; ++i) {
-            mbar_wait(dq_full, i & 1);
+            const int gq = n * nQ + i;
+            mbar_wait(dq_full, gq & 1);
             tc_fence_after();
 #pragma unroll
             for (int hfc = 0; hfc < 2; ++hfc) {       // 32 head-dim columns per pass through the staging tile
@@ -886,7 +921,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     bulk_commit();
                 }
             }
-            XQ_TR(i < 30 && qd == 0 && lane == 0, 16 * i + 12);
+            XQ_TR(gq < 30 && qd == 0 && lane == 0, 16 * gq + 12);
+        }
         }
         if (issuer) bulk_wait<0>();
     }
@@ -1150,24 +1186,23 @@ attn_dq_convert_kernel(const float *__restrict__ dq_acc, const __nv_bfloat16 *__
 }
 
 struct AttnBwdMaps {
-    const void *qkv, *dout, *dqkv, *acc;
+    const void *qkv, *dout, *acc;
     int B, N, H;
-    CUtensorMap tmQKV, tmDO, tmDQKV, tmDQ;
+    CUtensorMap tmQKV, tmDO, tmDQ;
 };
 
-static bool get_bwd_maps(const void *qkv, const void *dout, void *dqkv, void *acc, int B, int N, int H, AttnBwdMaps &m) {
+static bool get_bwd_maps(const void *qkv, const void *dout, void *acc, int B, int N, int H, AttnBwdMaps &m) {
     static std::mutex mu;
     static AttnBwdMaps cache[16];
     static int n_cached = 0, next = 0;
     std::lock_guard<std::mutex> g(mu);
     for (int i = 0; i < n_cached; ++i)
-        if (cache[i].qkv == qkv && cache[i].dout == dout && cache[i].dqkv == dqkv && cache[i].acc == acc && cache[i].B == B &&
+        if (cache[i].qkv == qkv && cache[i].dout == dout && cache[i].acc == acc && cache[i].B == B &&
             cache[i].N == N && cache[i].H == H) { m = cache[i]; return true; }
     AttnBwdMaps e;
-    e.qkv = qkv; e.dout = dout; e.dqkv = dqkv; e.acc = acc; e.B = B; e.N = N; e.H = H;
+    e.qkv = qkv; e.dout = dout; e.acc = acc; e.B = B; e.N = N; e.H = H;
     const uint64_t W = (uint64_t)3 * H * AT_D, Wo = (uint64_t)H * AT_D;
     if (!make_map_3d(&e.tmQKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(qkv), W, N, B, W * 2, (uint64_t)N * W * 2, AT_D, AT_BM)) return false;
-    if (!make_map_3d(&e.tmDQKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dqkv, W, N, B, W * 2, (uint64_t)N * W * 2, AT_D, AT_BM)) return false;
     if (!make_map_3d(&e.tmDO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(dout), Wo, N, B, Wo * 2, (uint64_t)N * Wo * 2, AT_D, AT_BM)) return false;
     if (!make_map_3d(&e.tmDQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, acc, AT_D, N, (uint64_t)B * H, AT_D * 4, (uint64_t)N * AT_D * 4, 32, AT_BM)) return false;
     cache[next] = e;
@@ -1225,7 +1260,7 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     float *deltaP = (float *)((char *)workspace + off_delta);
     float *dsT = (float *)((char *)workspace + off_dst);
     AttnBwdMaps m;
-    if (!get_bwd_maps(qkv, d_out, dqkv, acc, B, N, H, m)) return XQ_ERR_UNSUPPORTED;
+    if (!get_bwd_maps(qkv, d_out, acc, B, N, H, m)) return XQ_ERR_UNSUPPORTED;
     const int nt = attn_bwd_ktail(N);                                     // few trailing keys: CUDA-core kernel, not a key block
     const int nK = nt ? N / AT_BN : (N + AT_BN - 1) / AT_BN;
     const int Npad = (N + AT_BM - 1) / AT_BM * AT_BM;
@@ -1260,10 +1295,17 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
         XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const long long ctas = (long long)B * H * nK;
-    if (ctas > 0x7fffffffLL) return XQ_ERR_ARG;
-    attn_bwd_kernel<<<(unsigned)ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQKV, m.tmDQ, lseP, deltaP, g_bias, N, H, nK, Npad,
-                                                              c2, scale);
+    const long long items = (long long)B * H * nK;          // (batch*head, key block) work items of the persistent grid
+    if (items > 0x7fffffffLL) return XQ_ERR_ARG;
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        XQ_CUDA_TRY(cudaGetDevice(&dev));
+        XQ_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned ctas = (unsigned)(items < n_sms ? items : n_sms);
+    attn_bwd_kernel<<<ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQ, lseP, deltaP, (__nv_bfloat16 *)dqkv, g_bias, N, H, nK, Npad,
+                                                    (int)items, c2, scale);
     XQ_LAUNCH_CHECK("attn_bwd_kernel");
     {
         dim3 grid((unsigned)((N + AB_CONV_ROWS - 1) / AB_CONV_ROWS), (unsigned)(B * H));

@@ -32,6 +32,8 @@ t0 = t[16 * 30 + 2]
 names = ["mma:p_full", "mma:ds_full", "mma:dQ issued", "-", "wgE:S seen", "wgE:P done", "-", "-", "wgD:P seen", "wgD:dP seen", "wgD:dS done",
          "wgD:chunks done", "wgQ:drained", "wgD:ch0", "wgD:ch1", "wgD:ch2"]
 print("CTA 0 start -> end:", t[16 * 30 + 3] - t0, "clocks")
-for i in range(6):
+print("  kernel entry -> setup done:", t0 - t[16 * 30 + 4], " wgE0 reaches epilogue:", t[16 * 30 + 5] - t0, " dkv_done seen:", t[16 * 30 + 6] - t0,
+      " dV store issued:", t[16 * 30 + 7] - t0, " dV store + bias sums done:", t[16 * 30 + 8] - t0)
+for i in range(16):
     row = [(names[k], t[16 * i + k] - t0) for k in range(16) if t[16 * i + k]]
     print(f"i={i}: " + "  ".join(f"{n}={v}" for n, v in row))
