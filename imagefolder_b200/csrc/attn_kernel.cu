@@ -477,11 +477,11 @@ constexpr int AB_THREADS = 768;
 constexpr int AB_QS = 3;            // Q / dO ring stages (a stage is released only when dK_i retires: 2 stages starve the MMAs)
 
 struct AttnBwdSmem {
-    static constexpr int K = 0;
-    static constexpr int V = AT_TILE;
-    static constexpr int Q = 2 * AT_TILE;                   // AB_QS stages
-    static constexpr int DO = (2 + AB_QS) * AT_TILE;        // AB_QS stages
-    static constexpr int DS = (2 + 2 * AB_QS) * AT_TILE;    // 2 buffers x 2 row tiles
+    static constexpr int K = 0;                             // 2 buffers (item parity): the next item's K / V are prefetched
+    static constexpr int V = 2 * AT_TILE;                   // 2 buffers
+    static constexpr int Q = 4 * AT_TILE;                   // AB_QS stages
+    static constexpr int DO = (4 + AB_QS) * AT_TILE;        // AB_QS stages
+    static constexpr int DS = (4 + 2 * AB_QS) * AT_TILE;    // 2 row tiles (one per query half)
     static constexpr int DQ = (6 + 2 * AB_QS) * AT_TILE;    // fp32 staging: ONE row tile [128][32 fp32] (two passes per dQ_i)
     static constexpr int STAT = (7 + 2 * AB_QS) * AT_TILE;  // lse[AB_QS][128], delta[AB_QS][128]
     static constexpr int BAR = STAT + AB_QS * 1024;
@@ -494,23 +494,32 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                  : "memory");
 }
 
-// dV / dK epilogue of one item: the thread's accumulator row (64 fp32 from TMEM, already in o[]) * mul -> bf16 -> 128 contiguous
-// bytes of the packed gradient, and the column sums of the ROUNDED values of the warp's 32 rows -> qkv-bias gradient.  The sums
-// are a transpose-reduce butterfly over the warp (lane = row): 62 shuffles, after which lane l holds columns c0 and c0 + 1,
-// c0 = 32 b4 + 16 b3 + 8 b2 + 4 b1 + 2 b0 (bits of l) -> 2 atomics per lane.  The first butterfly step is fused with the rounding
-// (column chunk j and chunk j + 32 together) so that at most ~64 values are live.  Rows beyond N hold zeros (masked keys) and
-// are not stored.
-__device__ __forceinline__ void bwd_store_rows(uint32_t (&o)[64], float mul, __nv_bfloat16 *__restrict__ dst_row, bool row_ok,
-                                               float *__restrict__ g_bias_cols, int lane) {
+// dV / dK epilogue of one item: the thread's accumulator row (64 fp32 in TMEM at `taddr`) * mul -> bf16 -> 128 contiguous bytes
+// of the packed gradient, and the column sums of the ROUNDED values of the warp's 32 rows -> qkv-bias gradient.  The sums are a
+// transpose-reduce butterfly over the warp (lane = row): 62 shuffles, after which lane l holds columns c0 and c0 + 1,
+// c0 = 32 b4 + 16 b3 + 8 b2 + 4 b1 + 2 b0 (bits of l) -> 2 atomics per lane.  The row is read 8 + 8 columns at a time (column j
+// with column j + 32: the first butterfly step is fused with the rounding), so ~50 registers are live; `freed` is signalled as
+// soon as the last columns have left TMEM.  Rows beyond N hold zeros (masked keys) and are not stored.
+__device__ __forceinline__ void bwd_epilogue_rows(uint32_t taddr, float mul, __nv_bfloat16 *__restrict__ dst_row, bool row_ok,
+                                                  float *__restrict__ g_bias_cols, int lane, uint64_t *freed) {
     float a[32], b[16], c[8], d[4];
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
 #pragma unroll
     for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t lo[8], hi[8];
+        tmem_ld8(taddr + c8 * 8, lo);
+        tmem_ld8(taddr + 32 + c8 * 8, hi);
+        tmem_wait_ld();
+        if (c8 == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(freed);
+        }
         uint32_t wl[4], wh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            wl[e] = pack_bf16(__uint_as_float(o[c8 * 8 + 2 * e]) * mul, __uint_as_float(o[c8 * 8 + 2 * e + 1]) * mul);
-            wh[e] = pack_bf16(__uint_as_float(o[32 + c8 * 8 + 2 * e]) * mul, __uint_as_float(o[32 + c8 * 8 + 2 * e + 1]) * mul);
+            wl[e] = pack_bf16(__uint_as_float(lo[2 * e]) * mul, __uint_as_float(lo[2 * e + 1]) * mul);
+            wh[e] = pack_bf16(__uint_as_float(hi[2 * e]) * mul, __uint_as_float(hi[2 * e + 1]) * mul);
         }
         if (row_ok) {
             *reinterpret_cast<uint4 *>(dst_row + c8 * 8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
@@ -550,7 +559,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     XQ_TR(threadIdx.x == 0, 16 * 30 + 4);
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(base + AttnBwdSmem::BAR);
-    uint64_t *kv_full = bars + 0;
+    uint64_t *kv_full = bars + 19;    // [2] K / V buffers (item parity)
     uint64_t *q_full = bars + 1;      // [AB_QS] stages
     uint64_t *q_empty = bars + 4;     // [AB_QS]
     uint64_t *s_full = bars + 7;      // S^T_i in TMEM                      (MMA commit)
@@ -563,9 +572,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint64_t *dq_full = bars + 14;    // dQ_i partial in TMEM               (MMA commit)
     uint64_t *dq_free = bars + 15;    // dQ_i drained                       (4 warps of wgQ)
     uint64_t *dkv_done = bars + 16;   // dV / dK of the item complete          (MMA commit)
-    uint64_t *kv_free = bars + 17;    // last MMA reading K / V of the item retired (MMA commit): the tiles may be reloaded
+    uint64_t *kv_free = bars + 21;    // [2] last MMA reading this K / V buffer retired (MMA commit): it may be reloaded
     uint64_t *dkv_free = bars + 18;   // dV / dK of the item in registers      (4 warps of wgE0 + 4 of wgD0)
-    uint32_t *tmem_holder = (uint32_t *)(bars + 19);
+    uint32_t *tmem_holder = (uint32_t *)(bars + 23);
     float *s_lse = (float *)(base + AttnBwdSmem::STAT);          // [AB_QS][128]
     float *s_delta = s_lse + AB_QS * 128;                        // [AB_QS][128]
 
@@ -586,14 +595,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int nQ = Npad / AT_BM;
 
     if (tid == 0) {
-        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_free[i], 1); }
         for (int i = 0; i < AB_QS; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         mbar_init(s_full, 1); mbar_init(s_free, 8);
         mbar_init(p_full, 8); mbar_init(p_read, 8);
         mbar_init(dv_done, 1); mbar_init(dp_full, 1);
         mbar_init(ds_full, 8); mbar_init(dq_full, 1);
         mbar_init(dq_free, 4); mbar_init(dkv_done, 1);
-        mbar_init(kv_free, 1); mbar_init(dkv_free, 8);
+        mbar_init(dkv_free, 8);
         mbar_fence_init();
     }
     if (warp == 17) tmem_alloc<512>(tmem_holder);
@@ -619,15 +628,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 tma_prefetch_desc(&tmDO);
             }
             __syncwarp();
-            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+            // K / V of item n live in buffer n & 1; the next item's pair is requested while this item's third query block is being
+            // loaded (by then the last dQ MMA of item n-1, the previous user of that buffer, has all but retired), i.e. two to
+            // three blocks before its first MMA needs it: a TMA tile load was measured at ~5 k clk here.
+            auto load_kv = [&](int it, int n) {
                 const Item T = item_at(it);
-                if (n > 0) mbar_wait(kv_free, (n - 1) & 1);          // every MMA that reads the previous item's K / V has retired
+                const int kb = n & 1;
+                if (n >= 2) mbar_wait(&kv_free[kb], ((n >> 1) - 1) & 1);
                 if (elect_one()) {
-                    mbar_expect_tx(kv_full, 2 * AT_TILE);
-                    tma_load_3d(base + AttnBwdSmem::K, &tmQKV, T.colK, T.k0, T.b, kv_full);
-                    tma_load_3d(base + AttnBwdSmem::V, &tmQKV, T.colV, T.k0, T.b, kv_full);
+                    mbar_expect_tx(&kv_full[kb], 2 * AT_TILE);
+                    tma_load_3d(base + AttnBwdSmem::K + kb * AT_TILE, &tmQKV, T.colK, T.k0, T.b, &kv_full[kb]);
+                    tma_load_3d(base + AttnBwdSmem::V + kb * AT_TILE, &tmQKV, T.colV, T.k0, T.b, &kv_full[kb]);
                 }
                 __syncwarp();
+            };
+            if ((int)blockIdx.x < n_items) load_kv(blockIdx.x, 0);
+            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+                const Item T = item_at(it);
+                const int pre = min(2, nQ - 1);
                 for (int i = 0; i < nQ; ++i) {
                     const int g = n * nQ + i, st = g % AB_QS;
                     mbar_wait(&q_empty[st], ((g / AB_QS) & 1) ^ 1);
@@ -639,6 +657,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         bulk_load_1d(s_delta + st * 128, deltaP + (size_t)T.bh * Npad + i * AT_BM, 512, &q_full[st]);
                     }
                     __syncwarp();
+                    if (i == pre && it + (int)gridDim.x < n_items) load_kv(it + gridDim.x, n + 1);
                 }
             }
         } else if (warp == 17) {
@@ -646,17 +665,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             // program order per query block i:   S^T_{i+1}  |  dV += P^T_i dO_i  |  dK += dS^T_i Q_i ; dP^T_{i+1} ; dQ_i = dS_i K
             // (S^T_{i+1} only needs S^T_i to have left TMEM, so wgE never waits for it; dP^T_{i+1} is queued right behind
             //  dK_i -- which reads dS^T_i out of the same columns -- so wgD gets it back after two MMA groups)
-            const uint64_t kd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::K)), vd_k = desc_k_sw128(smem_u32(base + AttnBwdSmem::V));
-            const uint64_t kd_mn = desc_mn_sw128(smem_u32(base + AttnBwdSmem::K), 16384, 1024);
+            const uint64_t kd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::K)), vd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::V));
+            const uint64_t kd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::K), 16384, 1024);
             const uint64_t qd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::Q)), dd_k0 = desc_k_sw128(smem_u32(base + AttnBwdSmem::DO));
             const uint64_t qd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::Q), 16384, 1024);
             const uint64_t dd_mn0 = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DO), 16384, 1024);
             const uint64_t dsd = desc_mn_sw128(smem_u32(base + AttnBwdSmem::DS), AT_TILE, 1024);
             const uint32_t id_acc = idesc_bf16(AT_BN, AT_D, 0, 1);     // A from TMEM (K-major), B MN-major
             const uint32_t id_dq = idesc_bf16(AT_BM, AT_D, 1, 1);      // A, B MN-major smem
-            auto issue_s = [&](int i, int g) {
+            auto issue_s = [&](int i, int g, int kb) {
                 if (elect_one()) {
-                    const uint64_t qdk = desc_adv(qd_k0, (g % AB_QS) * AT_TILE);
+                    const uint64_t qdk = desc_adv(qd_k0, (g % AB_QS) * AT_TILE), kd_k = desc_adv(kd_k0, kb * AT_TILE);
                     const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
                     for (int k = 0; k < AT_D / 16; ++k) umma_ss(tS, desc_adv(kd_k, k * 32), desc_adv(qdk, k * 32), id, k > 0);
@@ -664,9 +683,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 __syncwarp();
             };
-            auto issue_dp = [&](int i, int g) {
+            auto issue_dp = [&](int i, int g, int kb) {
                 if (elect_one()) {
-                    const uint64_t ddk = desc_adv(dd_k0, (g % AB_QS) * AT_TILE);
+                    const uint64_t ddk = desc_adv(dd_k0, (g % AB_QS) * AT_TILE), vd_k = desc_adv(vd_k0, kb * AT_TILE);
                     const uint32_t id = idesc_bf16(AT_BN, nq_of(i), 0, 0);
 #pragma unroll
                     for (int k = 0; k < AT_D / 16; ++k) umma_ss(tDP, desc_adv(vd_k, k * 32), desc_adv(ddk, k * 32), id, k > 0);
@@ -674,24 +693,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 __syncwarp();
             };
-            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
-                const int g0 = n * nQ;
-                mbar_wait(kv_full, n & 1);
-                mbar_wait(&q_full[g0 % AB_QS], (g0 / AB_QS) & 1);
-                if (g0 > 0) mbar_wait(s_free, (g0 - 1) & 1);          // S^T of the previous item's last block has left TMEM
+            // one flat pipeline over (item n, query block i), global block counter g: the S^T and dP^T MMAs of the NEXT block are
+            // issued one block ahead also across an item boundary (the next item's K / V sit in the other buffer)
+            if ((int)blockIdx.x < n_items) {
+                mbar_wait(&kv_full[0], 0);
+                mbar_wait(&q_full[0], 0);
                 tc_fence_after();
-                issue_s(0, g0);
-                issue_dp(0, g0);          // dP^T columns: in program order behind the previous item's last dK MMA (their last reader)
+                issue_s(0, 0, 0);
+                issue_dp(0, 0, 0);
+            }
+            for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
+                const int g0 = n * nQ, kb = n & 1;
+                const bool next_item = it + (int)gridDim.x < n_items;
+                const uint64_t kd_mn = desc_adv(kd_mn0, kb * AT_TILE);
                 for (int i = 0; i < nQ; ++i) {
                     const int g = g0 + i, st = g % AB_QS;
                     const int ks = nq_of(i) / 16;
                     const uint64_t qd_mn = desc_adv(qd_mn0, st * AT_TILE), dd_mn = desc_adv(dd_mn0, st * AT_TILE);
-                    const bool more = i + 1 < nQ;
+                    const bool last = i + 1 == nQ;
+                    const bool more = !last || next_item;
+                    const int ni = last ? 0 : i + 1, nkb = last ? kb ^ 1 : kb;      // the block after this one
                     if (more) {
+                        if (last) mbar_wait(&kv_full[nkb], ((n + 1) >> 1) & 1);
                         mbar_wait(s_free, g & 1);
                         mbar_wait(&q_full[(g + 1) % AB_QS], ((g + 1) / AB_QS) & 1);
                         tc_fence_after();
-                        issue_s(i + 1, g + 1);
+                        issue_s(ni, g + 1, nkb);
                     }
                     mbar_wait(p_full, g & 1);
                     XQ_TR(g < 30 && lane == 0, 16 * g + 0);
@@ -710,31 +737,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         for (int k = 0; k < ks; ++k)      // dK += dS^T Q : each query half keeps its dS^T (bf16) over the start of its own dP^T columns
                             umma_ts(tDK, tDP + (k >> 2) * 64 + (k & 3) * 8, desc_adv(qd_mn, k * 2048), id_acc, (uint32_t)(i | k));
                         umma_commit(&q_empty[st]);        // Q_i / dO_i tiles are dead once dV_i and dK_i retire
+                        if (last) umma_commit(dkv_done);
                     }
                     __syncwarp();
-                    if (more) issue_dp(i + 1, g + 1);
+                    if (more) issue_dp(ni, g + 1, nkb);   // in program order behind dK_g, the last reader of these TMEM columns
                     if (g > 0) { mbar_wait(dq_free, (g - 1) & 1); tc_fence_after(); }
                     if (elect_one()) {
-                        const uint64_t dsi = desc_adv(dsd, (g & 1) * 2 * AT_TILE);
 #pragma unroll
                         for (int k = 0; k < AT_BN / 16; ++k)    // dQ_i = dS K : A = dS [M = q (2 row tiles), K = keys], B = K tile
-                            umma_ss(tDQ, desc_adv(dsi, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
+                            umma_ss(tDQ, desc_adv(dsd, k * 2048), desc_adv(kd_mn, k * 2048), id_dq, k > 0);
                         umma_commit(dq_full);
+                        if (last) umma_commit(&kv_free[kb]);     // every MMA that reads this item's K / V has been issued
                     }
                     __syncwarp();
                     XQ_TR(g < 30 && lane == 0, 16 * g + 2);
                 }
-                if (elect_one()) {
-                    umma_commit(dkv_done);
-                    umma_commit(kv_free);
-                }
-                __syncwarp();
             }
         }
     } else if (warp < 8) {
         reg_inc<88>();
         // ===== wgE (warps 0-7): P^T = exp2(S^T c - L2[q]); thread = (key row, query half hf): the MUFU warpgroups =====
         const int hf = warp >> 2;
+        // epilogue of item n (hf == 0 warps): dV (TMEM) -> registers (the accumulator is then free) -> bf16 -> global
+        auto epilogue_dv = [&](int it_e, int n_e) {
+            const Item E = item_at(it_e);
+            XQ_TR(n_e == 0 && tid == 0, 16 * 30 + 5);
+            mbar_wait(dkv_done, n_e & 1);
+            tc_fence_after();
+            XQ_TR(n_e == 0 && tid == 0, 16 * 30 + 6);
+            bwd_epilogue_rows(tDV + lane_addr, 1.0f, dqkv + ((size_t)E.b * N + E.k0 + krow) * (size_t)(3 * H * AT_D) + E.colV,
+                              E.k0 + krow < N, g_bias ? g_bias + E.colV : nullptr, lane, dkv_free);
+            XQ_TR(n_e == 0 && tid == 0, 16 * 30 + 8);
+        };
         for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
         const Item T = item_at(it);
         const bool key_ok = T.k0 + krow < N;
@@ -786,36 +820,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
             XQ_TR(gq < 30 && warp == 0 && lane == 0, 16 * gq + 5);
+            // the previous item's dV: its last dK MMA retires about now (this P^T was computed a block ahead), and the first dV
+            // MMA of this item waits for the accumulator to be in our registers (dkv_free)
+            if (hf == 0 && i == 0 && n > 0) epilogue_dv(it - gridDim.x, n - 1);
         }
-        if (hf == 0) {
-        // ---- epilogue of the item: dV (TMEM) -> registers (the accumulator is then free for the next item) -> bf16 -> global
-        XQ_TR(n == 0 && tid == 0, 16 * 30 + 5);
-        mbar_wait(dkv_done, n & 1);
-        tc_fence_after();
-        XQ_TR(n == 0 && tid == 0, 16 * 30 + 6);
-        uint32_t o[64];
-#pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 16) tmem_ld16(tDV + lane_addr + c0, *reinterpret_cast<uint32_t (*)[16]>(&o[c0]));
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
-        bwd_store_rows(o, 1.0f, dqkv + ((size_t)T.b * N + T.k0 + krow) * (size_t)(3 * H * AT_D) + T.colV, key_ok,
-                       g_bias ? g_bias + T.colV : nullptr, lane);
-        XQ_TR(n == 0 && tid == 0, 16 * 30 + 8);
         }
+        if (hf == 0 && n_items > (int)blockIdx.x) {
+            const int n_last = (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x;
+            epilogue_dv(blockIdx.x + n_last * gridDim.x, n_last);
         }
     } else if (warp < 16) {
         reg_inc<88>();
         // ===== wgD (warps 8-15): dS^T = P^T o (dP^T - delta[q]); thread = (key row, query half hf): the FMA warpgroups =====
         const int hf = (warp - 8) >> 2;
-        const uint32_t dsrow0 = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
+        const uint32_t dsrow = smem_u32(base + AttnBwdSmem::DS + hf * AT_TILE);
+        // epilogue of item n (hf == 0 warps): dK (TMEM) -> registers -> * scale -> bf16 -> global
+        auto epilogue_dk = [&](int it_e, int n_e) {
+            const Item E = item_at(it_e);
+            mbar_wait(dkv_done, n_e & 1);
+            tc_fence_after();
+            bwd_epilogue_rows(tDK + lane_addr, scale, dqkv + ((size_t)E.b * N + E.k0 + krow) * (size_t)(3 * H * AT_D) + E.colK,
+                              E.k0 + krow < N, g_bias ? g_bias + E.colK : nullptr, lane, dkv_free);
+        };
         for (int it = blockIdx.x, n = 0; it < n_items; it += gridDim.x, ++n) {
-        const Item T = item_at(it);
         for (int i = 0; i < nQ; ++i) {
             const int gq = n * nQ + i, st = gq % AB_QS;
-            const uint32_t dsrow = dsrow0 + (gq & 1) * 2 * AT_TILE;    // double-buffered dS operand of the dQ MMA
             const int nqr = nq_of(i);
+            // the previous item's dK: these warps would only wait for P^T of this block here (wgE is still computing it)
+            if (hf == 0 && i == 0 && n > 0) epilogue_dk(it - gridDim.x, n - 1);
             mbar_wait(&q_full[st], (gq / AB_QS) & 1);
             mbar_wait(p_full, gq & 1);
             XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 8);
@@ -828,8 +860,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (lane == 0) mbar_arrive(p_read);
             mbar_wait(dp_full, gq & 1);
             XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 9);
-            // this dS buffer was last read by the dQ_{i-2} MMA (long retired: dq_full(i-2) completed before dq_free(i-2), which the
-            // MMA warp waited for before issuing dQ_{i-1}, which precedes dP^T_i in its program order)
+            // the dS operand tile in shared memory is single-buffered (the second buffer went to the K / V prefetch): dQ_{g-1},
+            // its last reader, must have retired
+            if (gq > 0) mbar_wait(dq_full, (gq - 1) & 1);
             tc_fence_after();
             const uint32_t d4 = smem_u32(s_delta + st * 128 + hf * 64);
 #pragma unroll
@@ -872,20 +905,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (lane == 0) mbar_arrive(ds_full);
             XQ_TR(gq < 30 && warp == 8 && lane == 0, 16 * gq + 10);
         }
-        if (hf == 0) {
-        // ---- epilogue of the item: dK (TMEM) -> registers -> * scale -> bf16 -> global
-        mbar_wait(dkv_done, n & 1);
-        tc_fence_after();
-        uint32_t o[64];
-#pragma unroll
-        for (int c0 = 0; c0 < AT_D; c0 += 16) tmem_ld16(tDK + lane_addr + c0, *reinterpret_cast<uint32_t (*)[16]>(&o[c0]));
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
-        bwd_store_rows(o, scale, dqkv + ((size_t)T.b * N + T.k0 + krow) * (size_t)(3 * H * AT_D) + T.colK, T.k0 + krow < N,
-                       g_bias ? g_bias + T.colK : nullptr, lane);
         }
+        if (hf == 0 && n_items > (int)blockIdx.x) {
+            const int n_last = (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x;
+            epilogue_dk(blockIdx.x + n_last * gridDim.x, n_last);
         }
     } else {
         reg_dec<56>();
