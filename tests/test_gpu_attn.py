@@ -23,7 +23,10 @@ def _ref(qkv32, H):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 513, 3), (2, 514, 2), (1, 769, 2), (2, 499, 2), (2, 379, 3), (3, 1, 1), (1, 16, 2),
-                                   (2, 128, 2), (2, 129, 1), (1, 1024, 1), (1, 333, 12)])
+                                   (2, 128, 2), (2, 129, 1), (1, 1024, 1), (1, 333, 12),
+                                   # more (batch*head, key block) items than SMs: every CTA of the persistent backward walks
+                                   # several items (K / V prefetch into the other buffer, epilogue pipelined into the next item)
+                                   (5, 513, 12), (7, 300, 12), (40, 130, 12), (13, 100, 12)])
 @pytest.mark.parametrize("amp", [1.0, 2.5])
 def test_attention_forward_backward_match_fp32_reference(B, N, H, amp):
     from imagefolder_b200 import vit_ops
@@ -47,6 +50,11 @@ def test_attention_forward_backward_match_fp32_reference(B, N, H, amp):
         m = max(1e-3, gr[:, :, i].abs().max().item())
         err = (d[:, :, i] - gr[:, :, i]).abs().max().item()
         assert err <= 1e-2 * m, f"d{name}: err {err:.3e} vs max {m:.3e}"
+    # the fused qkv-bias gradient = column sums of the ROUNDED packed gradient the same call wrote
+    dq2, db = vit_ops.attn_tc_backward(qkv, out, lse2, g, H, want_bias_grad=True)
+    torch.cuda.synchronize()
+    want = dq2.float().sum((0, 1))
+    assert (db - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item()) + 1e-4 * B * N ** 0.5
 
 
 def test_attention_autograd_node_uses_the_tc_kernels_and_matches_sdpa():
