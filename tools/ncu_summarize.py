@@ -49,7 +49,7 @@ def main():
         if rd and wr:
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot = rd[0] * scale.get(rd[1], 1) + wr[0] * scale.get(wr[1], 1)
-            short = name.split("(")[0].split("::")[-1]
+            short = name.split("(")[0].split("<")[0].split("::")[-1].replace("void ", "")
             traffic[f"{short}/{tag}" if tag else short] = tot
             lines.append(f"| **dram traffic / launch** | {tot / 1e6:.1f} MB |")
     open(out_md, "w").write("\n".join(lines) + "\n")
