@@ -465,11 +465,7 @@ def run_ours(a):
         "metric": METRIC, "value": world * B * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{a.workload} tokenizer training step, per-GPU batch {B}, 256x256, ViT-B enc/dec, "
-                               "fwd+bwd+AdamW, L2+vq+commit loss (no LPIPS/GAN/teacher)",
-                   "global_batch": world * B, "parallelism": f"dp{world}",
-                   "grad_allreduce": ("none (1 GPU)" if world == 1 else ("fp32 buckets" if a.fp32_grads else "bf16-compressed buckets (fp32 master weights)")),
-                   "l2_policy": "inputs (201 MB/step) + activations exceed the 126 MB L2"},
+        "config": workload_config(a, world),
         "e2e": {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": imgs_host.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps,
                 "step_ms": e2e_steps},
@@ -527,6 +523,17 @@ def cpu_arm(a, steps, warmup, state=None, margs=None, budget_s=14.0):
                       f"C oracle quantizer), {dt:.1f} s", "ms_per_step": dt / steps * 1e3}
 
 
+def workload_config(a, world):
+    """the `config` object of a bench line: both arms print the SAME object for the same command line (the reference arm times a
+    bounded sample of this workload on the host cores and says so in its `cpu_baseline.sample` / `note`)"""
+    B = a.batch
+    return {"workload": f"{a.workload} tokenizer training step, per-GPU batch {B}, 256x256, ViT-B enc/dec, "
+                        "fwd+bwd+AdamW, L2+vq+commit loss (no LPIPS/GAN/teacher)",
+            "global_batch": world * B, "parallelism": f"dp{world}",
+            "grad_allreduce": ("none (1 GPU)" if world == 1 else ("fp32 buckets" if a.fp32_grads else "bf16-compressed buckets (fp32 master weights)")),
+            "l2_policy": "inputs (201 MB/step) + activations exceed the 126 MB L2"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -536,8 +543,10 @@ def run_reference(a):
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": base["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{a.workload} tokenizer training step on host cores (oracle port of the reference "
-                                  "path; the reference itself is Python + un-vendored timm and cannot travel)"},
+           "config": workload_config(a, max(1, a.gpus)),
+           "note": "host-core arm: the oracle port of the reference path (torch-CPU ViT + C oracle quantizer, fp32) on a bounded "
+                   "sample of the workload above; the reference itself is Python + un-vendored timm and cannot travel.  Rank 0 "
+                   "only; the GPU-specific config keys describe the arm it is compared with",
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
