@@ -428,6 +428,25 @@ struct AttnMaps {
     CUtensorMap tmQKV, tmO;
 };
 
+// per-device one-time setup (function attributes are per device; the SM count may differ between devices of one process)
+struct AttnDevState { bool fwd_attr = false, bwd_attr = false, prep_attr = false; int n_sms = 0; };
+static int attn_dev_state(AttnDevState **out) {
+    static std::mutex mu;
+    static AttnDevState states[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return xq::record_cuda_error(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return XQ_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> g(mu);
+    AttnDevState &s = states[dev];
+    if (!s.n_sms) {
+        e = cudaDeviceGetAttribute(&s.n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return xq::record_cuda_error(e, "cudaDeviceGetAttribute");
+    }
+    *out = &s;
+    return XQ_OK;
+}
+
 static bool get_fwd_maps(const void *qkv, void *out, int B, int N, int H, AttnMaps &m) {
     static std::mutex mu;
     static AttnMaps cache[16];
@@ -1290,18 +1309,19 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
     if ((long long)B * H > 65535) return XQ_ERR_UNSUPPORTED;
     if (g_bias) XQ_CUDA_TRY(cudaMemsetAsync(g_bias, 0, (size_t)3 * H * AT_D * sizeof(float), st));
     const float c2 = scale * 1.4426950408889634f;
+    AttnDevState *ds = nullptr;
+    if (int rc = attn_dev_state(&ds)) return rc;
     {
         dim3 grid(nt ? 1u : (unsigned)(Npad / AB_PREP_ROWS), (unsigned)(B * H));
         const __nv_bfloat16 *qp = (const __nv_bfloat16 *)qkv, *op = (const __nv_bfloat16 *)out, *gp = (const __nv_bfloat16 *)d_out;
         __nv_bfloat16 *dp = (__nv_bfloat16 *)dqkv;
         constexpr int PS = 2 * 3 * (AB_PREP_ROWS / 32) * 256 * 16;             // the NT > 0 variants' two-stage row buffer
-        static bool prep_attr = false;
-        if (!prep_attr) {
+        if (!ds->prep_attr) {
             XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
             XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
             XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
             XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_prep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS));
-            prep_attr = true;
+            ds->prep_attr = true;
         }
         switch (nt) {
         case 0: attn_bwd_prep_kernel<0><<<grid, 256, 0, st>>>(qp, op, gp, lse2, lseP, deltaP, acc, dsT, dp, g_bias, N, H, Npad, c2, scale); break;
@@ -1313,20 +1333,13 @@ int xq_vit_attn_bwd(const void *qkv, const void *out, const void *d_out, const f
         XQ_LAUNCH_CHECK("attn_bwd_prep_kernel");
     }
     const size_t smem = AttnBwdSmem::BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ds->bwd_attr) {
         XQ_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ds->bwd_attr = true;
     }
     const long long items = (long long)B * H * nK;          // (batch*head, key block) work items of the persistent grid
     if (items > 0x7fffffffLL) return XQ_ERR_ARG;
-    static int n_sms = 0;
-    if (!n_sms) {
-        int dev = 0;
-        XQ_CUDA_TRY(cudaGetDevice(&dev));
-        XQ_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const unsigned ctas = (unsigned)(items < n_sms ? items : n_sms);
+    const unsigned ctas = (unsigned)(items < ds->n_sms ? items : ds->n_sms);
     attn_bwd_kernel<<<ctas, AB_THREADS, smem, st>>>(m.tmQKV, m.tmDO, m.tmDQ, lseP, deltaP, (__nv_bfloat16 *)dqkv, g_bias, N, H, nK, Npad,
                                                     (int)items, c2, scale);
     XQ_LAUNCH_CHECK("attn_bwd_kernel");
@@ -1356,14 +1369,12 @@ int xq_vit_attn_fwd(const void *qkv, void *out, float *lse2, int B, int N, int H
     const int n_tail = (N % AT_BM != 0 && N % AT_BM <= AT_TAIL_MAX && N > AT_BM) ? N % AT_BM : 0;
     const int nQ = n_tail ? N / AT_BM : (N + AT_BM - 1) / AT_BM;
     const size_t smem = AttnFwdSmem::BYTES + 1024;
-    static bool attr_set = false;
-    static int n_sm = 0;
-    if (!attr_set) {
+    AttnDevState *ds = nullptr;
+    if (int rc = attn_dev_state(&ds)) return rc;
+    const int n_sm = ds->n_sms;
+    if (!ds->fwd_attr) {
         XQ_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        XQ_CUDA_TRY(cudaGetDevice(&dev));
-        XQ_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        ds->fwd_attr = true;
     }
     const long long tiles = (long long)B * H * nQ;
     if (tiles > 0x7fffffffLL) return XQ_ERR_ARG;
