@@ -193,6 +193,43 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 // ---- explicit shared-memory accesses (pointers derived from the aligned dynamic-smem base are GENERIC to the compiler:
 // without these it emits ST.E / LD.E generic instructions instead of STS / LDS) ------------------------------------
+// ---- CTA pair (cta_group::2): two CTAs of a 2-cluster (same TPC) issue ONE MMA with M = 256 (128 accumulator rows in each
+// CTA's TMEM) and N <= 256 (each CTA stages half of the B tile).  PTX forms as in the vendored CUTLASS headers
+// (cute/arch/copy_sm100_tma.hpp, cutlass/arch/barrier.h, cute/arch/tmem_allocator_sm100.hpp); verified on hardware by
+// tools/gemm_probe.cu (bit-identical to cuBLAS at 131328 x 3072 x 768).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by BOTH CTAs: the bytes land in the executing CTA's shared memory and complete on the LEADER's (rank 0) barrier --
+// the mbarrier address with the pair's peer bit cleared
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *leader_bar) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar, uint32_t cta) {       // arrive on `bar` of cluster CTA `cta`
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t *bar) {                         // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t *smem_holder) {                  // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
+}
+
 __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

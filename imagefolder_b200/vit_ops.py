@@ -120,6 +120,75 @@ def gelu_bias(x, bias=None):
     return _GeluBias.apply(x, bias)
 
 
+MLP_TC_ENABLED = [True]       # the tcgen05 GEMMs with fused GELU / GELU' epilogues (csrc/gemm_kernel.cu)
+
+
+def mlp_tc_ok(y, fc1, fc2) -> bool:
+    """xq_vit_fc1_gelu_fwd / xq_vit_fc2_dgelu_bwd cover the shipped widths: bf16 tokens, hidden % 256 == 0, embed % 64 == 0."""
+    return (MLP_TC_ENABLED[0] and y.is_cuda and y.dtype == torch.bfloat16 and fc1.bias is not None
+            and fc1.weight.shape[0] % 256 == 0 and fc1.weight.shape[1] % 64 == 0 and fc1.weight.shape[0] // 256 <= 64
+            and fc2.weight.shape[1] == fc1.weight.shape[0] and fc2.weight.shape[0] % 8 == 0)
+
+
+class _FusedMLP(torch.autograd.Function):
+    """branch = fc2(GELU(fc1(y)))  WITHOUT the fc2 bias (folded into the next residual_ln), timm Mlp as called from Block.forward
+    (dino_enc/vision_transformer.py:336-339).  The fc1 GEMM carries bias + GELU in its epilogue, the fc2 input-gradient GEMM carries
+    GELU' and the fc1-bias gradient; the other GEMMs are library calls.  Same bits as F.linear + gelu_bias (the epilogues apply
+    the same device functions to the same rounded bf16 values)."""
+
+    @staticmethod
+    def forward(ctx, y, W1, b1, W2):
+        K = W1.shape[1]
+        N = W1.shape[0]
+        y2 = y.reshape(-1, K)
+        if not y2.is_contiguous():
+            y2 = y2.contiguous()
+        M = y2.shape[0]
+        W1b = W1.to(torch.bfloat16)
+        W2b = W2.to(torch.bfloat16)
+        b1f = b1.float()
+        pre = torch.empty(M, N, dtype=torch.bfloat16, device=y.device)
+        act = torch.empty(M, N, dtype=torch.bfloat16, device=y.device)
+        L = C.lib()
+        C.call("xq_vit_fc1_gelu_fwd", 1, L.xq_vit_fc1_gelu_fwd, C.ptr(y2), C.ptr(W1b), C.ptr(b1f), C.ptr(pre), C.ptr(act), M, N, K,
+               C.stream_ptr(y.device), nbytes=M * K * 2 + N * K * 2 + M * N * 4, nflops=2.0 * M * N * K)
+        branch = act @ W2b.t()
+        ctx.save_for_backward(y2, pre, act, W1b, W2b, b1f)
+        ctx.out_shape = y.shape[:-1] + (W2.shape[0],)
+        ctx.in_shape = y.shape
+        return branch.view(ctx.out_shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        y2, pre, act, W1b, W2b, b1f = ctx.saved_tensors
+        M, N = pre.shape
+        Ko = W2b.shape[0]
+        g2 = g.reshape(M, Ko)
+        if g2.dtype != torch.bfloat16:
+            g2 = g2.to(torch.bfloat16)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dW2 = (g2.t() @ act).float() if ctx.needs_input_grad[3] else None
+        W2t = W2b.t().contiguous()                      # [hidden, out]: the K-major B operand of d_act = g W2
+        dpre = torch.empty_like(pre)
+        db1 = torch.empty(N, dtype=torch.float32, device=pre.device)
+        L = C.lib()
+        C.call("xq_vit_fc2_dgelu_bwd", 1, L.xq_vit_fc2_dgelu_bwd, C.ptr(g2), C.ptr(W2t), C.ptr(pre), C.ptr(b1f), C.ptr(dpre), C.ptr(db1),
+               M, N, Ko, C.stream_ptr(pre.device), nbytes=M * Ko * 2 + N * Ko * 2 + M * N * 4, nflops=2.0 * M * N * Ko)
+        dW1 = (dpre.t() @ y2).float() if ctx.needs_input_grad[1] else None
+        dy = (dpre @ W1b).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        return dy, dW1, (db1 if ctx.needs_input_grad[2] else None), dW2
+
+
+def mlp_forward(mlp, y):
+    """timm Mlp (fc1 -> GELU -> fc2, drop = 0) without the fc2 bias; fused tcgen05 path when the shapes allow, else library GEMMs +
+    the stand-alone bias / GELU kernel."""
+    if mlp_tc_ok(y, mlp.fc1, mlp.fc2):
+        return _FusedMLP.apply(y, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight)
+    h = gelu_bias(F.linear(y, mlp.fc1.weight), mlp.fc1.bias)
+    return F.linear(h, mlp.fc2.weight)
+
+
 ATTN_TC_ENABLED = [True]      # the tcgen05 attention kernels (csrc/attn_kernel.cu); tools flip it to time the library path
 
 
@@ -446,8 +515,7 @@ def run_blocks(vit, x, attn_mask=None):
         g1 = blk.ls1.gamma if hasattr(blk.ls1, "gamma") else None
         x, y = residual_ln(x, a, blk.attn.proj.bias if plain_attn else None, g1,
                            _droppath_scale(blk.drop_path1, Bn, dev), blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-        h = gelu_bias(F.linear(y, blk.mlp.fc1.weight), blk.mlp.fc1.bias)     # fc1 bias folded into the GELU kernel
-        branch = F.linear(h, blk.mlp.fc2.weight)                             # fc2 bias folded into the next residual_ln
+        branch = mlp_forward(blk.mlp, y)          # fc1 bias in the GELU epilogue / kernel; fc2 bias folded into the next residual_ln
         bias = blk.mlp.fc2.bias
         gamma = blk.ls2.gamma if hasattr(blk.ls2, "gamma") else None
         rs = _droppath_scale(blk.drop_path2, Bn, dev)

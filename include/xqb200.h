@@ -282,6 +282,19 @@ int xq_diffaug_forward(const float *x, const float *rand01, int B, int C, int H,
 int xq_diffaug_backward(const float *g, const float *rand01, int B, int C, int H, int W, int flags, int cut_h, int cut_w,
                         float *gx, float *sums, void *stream);
 
+/* ---- ViT MLP with the element-wise work fused into a hand-written tcgen05 GEMM (csrc/gemm_kernel.cu) --------------------
+ * Replaces, inside timm's Mlp as called by Block.forward (tokenizer/tokenizer_image/dino_enc/vision_transformer.py:336-339):
+ *   forward   F.linear(y, W1) [cuBLAS] + GELU(. + b1) [xq_vit_gelu_fwd]            -> xq_vit_fc1_gelu_fwd
+ *   backward  d_act = d_out W2 [cuBLAS] + d_act * GELU'(pre + b1), d_b1 [xq_vit_gelu_bwd] -> xq_vit_fc2_dgelu_bwd
+ * All matrices row-major bf16; bias / d_bias fp32.  N % 256 == 0, K % 64 == 0 (else XQ_ERR_UNSUPPORTED: the caller keeps the
+ * library GEMM + stand-alone kernel), any M.  Results are bit-identical to that two-call sequence.
+ *   x [M,K], w [N,K] (fc1.weight as bf16)  ->  pre [M,N] = x w^T ,  act [M,N] = GELU(pre + bias)                               */
+int xq_vit_fc1_gelu_fwd(const void *x, const void *w, const float *bias, void *pre, void *act, int M, int N, int K, void *stream);
+/*  d_out [M,K] (gradient of the fc2 output), w2t [N,K] (fc2.weight TRANSPOSED, bf16), pre [M,N] (saved by the forward)
+ *   ->  d_pre [M,N] = (d_out w2t^T) * GELU'(pre + bias) ,  d_bias [N] = column sums of the rounded d_pre                      */
+int xq_vit_fc2_dgelu_bwd(const void *d_out, const void *w2t, const void *pre, const float *bias, void *d_pre, float *d_bias,
+                         int M, int N, int K, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

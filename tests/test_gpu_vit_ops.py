@@ -293,3 +293,43 @@ def test_assemble_cabi_exact():
         gs, gt = torch.autograd.grad(out, (src, table), g)
         assert gs.dtype == dt and torch.equal(gs, g[:, 3:10].to(dt))
         np.testing.assert_allclose(gt.cpu().numpy(), g.sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,C,Hd", [(2 * 513, 384, 1536), (4 * 513, 768, 3072), (131, 768, 3072), (3 * 256, 384, 1536)])
+def test_fused_mlp_gemm_epilogues_equal_library_gemm_plus_gelu_kernels(M, C, Hd):
+    """xq_vit_fc1_gelu_fwd / xq_vit_fc2_dgelu_bwd (tcgen05 cta_group::2 GEMMs with GELU / GELU' + bias-gradient epilogues) against the
+    path they replace -- library GEMM + the stand-alone bias / GELU kernels -- for timm Mlp inside Block.forward
+    (dino_enc/vision_transformer.py:336-339).  The epilogues apply the same device functions to the same rounded bf16 values, so the
+    results agree to the last bit up to the accumulation order of the GEMMs (checked at bf16 resolution)."""
+    from imagefolder_b200 import vit_ops
+    torch.manual_seed(M + C)
+    dev = torch.device("cuda")
+    mlp = torch.nn.Module()
+    mlp.fc1 = torch.nn.Linear(C, Hd).to(dev)
+    mlp.fc2 = torch.nn.Linear(Hd, C).to(dev)
+    y0 = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    g = torch.randn(M, C, device=dev).to(torch.bfloat16)
+
+    def run(fused):
+        vit_ops.MLP_TC_ENABLED[0] = fused
+        for p in mlp.parameters():
+            p.grad = None
+        y = y0.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = vit_ops.mlp_forward(mlp, y)
+        out.backward(g)
+        return out.detach(), y.grad, mlp.fc1.weight.grad, mlp.fc1.bias.grad, mlp.fc2.weight.grad
+
+    try:
+        assert vit_ops.mlp_tc_ok(y0, mlp.fc1, mlp.fc2)
+        a = run(True)
+        b = run(False)
+    finally:
+        vit_ops.MLP_TC_ENABLED[0] = True
+    torch.cuda.synchronize()
+    names = ["branch", "d_y", "d_W1", "d_b1", "d_W2"]
+    for n, u, v in zip(names, a, b):
+        assert u.shape == v.shape and torch.isfinite(u.float()).all(), n
+        scale = max(1e-6, v.float().abs().max().item())
+        err = (u.float() - v.float()).abs().max().item()
+        assert err <= 8e-3 * scale, f"{n}: max err {err:.3e} vs max {scale:.3e}"
