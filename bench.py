@@ -386,7 +386,9 @@ def run_ours(a):
     if a.impl == "ours" and vit_ops.ATTN_TC_ENABLED[0]:
         # the fused path must be the one that ran (a silent library fallback would hide behind the step time)
         names = {r["entry"] for r in kern_table}
-        assert {"xq_vit_attn_fwd", "xq_vit_attn_bwd", "xq_vit_residual_ln_fwd", "xq_vit_gelu_fwd"} <= names, names
+        want = {"xq_vit_attn_fwd", "xq_vit_attn_bwd", "xq_vit_residual_ln_fwd"}
+        want |= {"xq_vit_fc1_gelu_fwd", "xq_vit_fc2_dgelu_bwd"} if vit_ops.MLP_TC_ENABLED[0] else {"xq_vit_gelu_fwd"}
+        assert want <= names, names
 
     # ---- timed region 2: end to end through the public API with HOST buffers
     # one-off setup outside the clock (a data loader allocates its pinned buffers and copy stream once; cudaHostAlloc

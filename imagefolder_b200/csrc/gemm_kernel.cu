@@ -62,15 +62,21 @@ __device__ __forceinline__ void gm_store_rows(uint32_t stg, const uint32_t (&w)[
     }
     __syncwarp();
 }
-// global rows -> staging -> this thread's row (rows >= rows_ok read as zero)
-__device__ __forceinline__ void gm_load_rows(uint32_t stg, uint32_t (&w)[16], const __nv_bfloat16 *__restrict__ gbase, size_t ld,
-                                             int rows_ok, int lane) {
+// global rows -> registers in the coalesced view (rows >= rows_ok read as zero): issued one chunk AHEAD of its use
+__device__ __forceinline__ void gm_prefetch_rows(uint4 (&pf)[4], const __nv_bfloat16 *__restrict__ gbase, size_t ld, int rows_ok, int lane) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), c = lane & 3;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < rows_ok) v = *reinterpret_cast<const uint4 *>(gbase + (size_t)r * ld + c * 8);
-        sts128(stg + gm_stg_off(r, c), v);
+        pf[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows_ok) pf[i] = *reinterpret_cast<const uint4 *>(gbase + (size_t)r * ld + c * 8);
+    }
+}
+// prefetched registers -> staging -> this thread's row
+__device__ __forceinline__ void gm_load_rows(uint32_t stg, uint32_t (&w)[16], const uint4 (&pf)[4], int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), c = lane & 3;
+        sts128(stg + gm_stg_off(r, c), pf[i]);
     }
     __syncwarp();
 #pragma unroll
@@ -170,6 +176,11 @@ mlp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float bsum[GM_CW / 32];
 #pragma unroll
         for (int i = 0; i < GM_CW / 32; ++i) bsum[i] = 0.f;
+        // backward: the stored pre-activation of the NEXT 32 x 32 chunk is fetched while the current one is computed (and the first
+        // chunk of a tile while its MMAs are still running)
+        uint4 pf[4];
+        auto tile_base = [&](int mb) { return (size_t)(mb * 2 * GM_BM + (int)rank * GM_BM + qd * 32) * N + nb * GM_BN + grp * GM_CW; };
+        if (EPI == 2 && mb0 < nM) gm_prefetch_rows(pf, C2 + tile_base(mb0), N, M - (mb0 * 2 * GM_BM + (int)rank * GM_BM + qd * 32), lane);
         for (int mb = mb0; mb < nM; mb += mstep, ++tc) {
             const int as = tc & 1;
             const int r0 = mb * 2 * GM_BM + (int)rank * GM_BM + qd * 32;        // first of this warp's 32 rows
@@ -206,7 +217,12 @@ mlp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 } else {
                     float cs[32];
                     uint32_t xin[16], wo[16];
-                    gm_load_rows(stg, xin, C2 + row_w + c0, N, rows_ok, lane);
+                    gm_load_rows(stg, xin, pf, lane);
+                    if (c0 + 32 < GM_CW) {
+                        gm_prefetch_rows(pf, C2 + row_w + c0 + 32, N, rows_ok, lane);
+                    } else if (mb + mstep < nM) {
+                        gm_prefetch_rows(pf, C2 + tile_base(mb + mstep), N, M - ((mb + mstep) * 2 * GM_BM + (int)rank * GM_BM + qd * 32), lane);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 b0 = lds128f(sb + (c0 + 8 * q) * 4), b1 = lds128f(sb + (c0 + 8 * q + 4) * 4);
