@@ -27,8 +27,9 @@
 namespace xq {
 
 using namespace xqtc;
-using xqv::dgelu_f;
-using xqv::gelu_f;
+using xqv::dgelu_f2;
+using xqv::gelu_f2;
+using xqv::up2;
 
 constexpr int GM_BM = 128, GM_BN = 256, GM_BK = 64;            // per CTA: 128 rows; per pair: 256 x 256
 constexpr int GM_NEPI = 16;                                    // epilogue warps (4 per SM sub-partition)
@@ -209,7 +210,9 @@ mlp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const uint32_t pre = pack_bf16(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]));
                             const float x0 = __uint_as_float(pre << 16) + bb[2 * e], x1 = __uint_as_float(pre & 0xffff0000u) + bb[2 * e + 1];
                             wp[4 * q + e] = pre;
-                            wa[4 * q + e] = pack_bf16(gelu_f(x0), gelu_f(x1));
+                            float y0, y1;
+                            up2(gelu_f2(x0, x1), y0, y1);
+                            wa[4 * q + e] = pack_bf16(y0, y1);
                         }
                     }
                     gm_store_rows(stg, wp, C + row_w + c0, N, rows_ok, lane);
@@ -234,7 +237,9 @@ mlp_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const uint32_t gh = pack_bf16(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1]));
                             const uint32_t xs = xin[4 * q + e];
                             const float x0 = __uint_as_float(xs << 16) + bb[2 * e], x1 = __uint_as_float(xs & 0xffff0000u) + bb[2 * e + 1];
-                            const uint32_t o = pack_bf16(__uint_as_float(gh << 16) * dgelu_f(x0), __uint_as_float(gh & 0xffff0000u) * dgelu_f(x1));
+                            float d0, d1;
+                            up2(dgelu_f2(x0, x1), d0, d1);
+                            const uint32_t o = pack_bf16(__uint_as_float(gh << 16) * d0, __uint_as_float(gh & 0xffff0000u) * d1);
                             wo[4 * q + e] = o;
                             cs[8 * q + 2 * e] = __uint_as_float(o << 16);
                             cs[8 * q + 2 * e + 1] = __uint_as_float(o & 0xffff0000u);
