@@ -150,3 +150,31 @@ def test_attention_entry_points_validate_arguments_without_gpu():
     assert L.xq_vit_attn_bwd(None, None, None, None, None, None, 1, 16, 1, 64, 0.125, None, 0, None) == -1
     assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, None, 2, 513, 12, 64, 0.125, 4096, need - 1, None) == -2   # workspace
     assert L.xq_vit_attn_bwd(4096, 4096, 4096, 4096, 4096, None, 2, 513, 12, 128, 0.125, 4096, need, None) == -4
+
+
+def test_fused_mlp_gemm_entry_points_validate_arguments_without_gpu():
+    """xq_vit_fc1_gelu_fwd / xq_vit_fc2_dgelu_bwd (csrc/gemm_kernel.cu): NULL pointers, misaligned buffers and widths the CTA-pair
+    tile does not cover are refused before anything is launched (the host then keeps library GEMM + the stand-alone kernel)."""
+    import ctypes as C
+    from imagefolder_b200 import _capi
+    L = _capi.lib()
+    f = C.cast(C.c_void_p(4096), C.POINTER(C.c_float))
+    assert L.xq_vit_fc1_gelu_fwd(None, 4096, f, 4096, 4096, 128, 3072, 768, None) == -1
+    assert L.xq_vit_fc1_gelu_fwd(4096, 4096, f, 4096, 4096, 0, 3072, 768, None) == -1            # M = 0
+    assert L.xq_vit_fc1_gelu_fwd(4096, 4096, f, 4096, 4096, 128, 3000, 768, None) == -4          # N % 256 != 0: unsupported
+    assert L.xq_vit_fc1_gelu_fwd(4096, 4096, f, 4096, 4096, 128, 3072, 100, None) == -4          # K % 64 != 0: unsupported
+    assert L.xq_vit_fc1_gelu_fwd(4100, 4096, f, 4096, 4096, 128, 3072, 768, None) == -1          # x not 16-byte aligned
+    assert L.xq_vit_fc2_dgelu_bwd(4096, 4096, 4096, f, 4096, None, 128, 3072, 768, None) == -1   # no bias-gradient buffer
+    assert L.xq_vit_fc2_dgelu_bwd(4096, None, 4096, f, 4096, f, 128, 3072, 768, None) == -1
+    assert L.xq_vit_fc2_dgelu_bwd(4096, 4096, 4096, f, 4096, f, 128, 1000, 768, None) == -4
+
+
+def test_fused_mlp_dispatch_conditions():
+    """vit_ops.mlp_tc_ok: the fused GEMMs take bf16 CUDA tokens with hidden % 256 == 0 and embed % 64 == 0; everything else stays on
+    library GEMM + stand-alone bias / GELU kernel (same results, tests/test_gpu_vit_ops.py)."""
+    import torch
+    from imagefolder_b200 import vit_ops
+    fc1, fc2 = torch.nn.Linear(768, 3072), torch.nn.Linear(3072, 768)
+    y = torch.zeros(4, 768, dtype=torch.bfloat16)
+    assert not vit_ops.mlp_tc_ok(y, fc1, fc2)                          # CPU tensor: never
+    assert vit_ops.MLP_TC_ENABLED[0] is True
