@@ -107,7 +107,8 @@ class ClockSampler:
 # C-ABI entry point -> the kernel that dominates it (the name ncu reports; key of profiles/ncu_traffic.json)
 ENTRY_MAIN_KERNEL = {"xq_vit_attn_bwd": "attn_bwd_kernel", "xq_vit_attn_fwd": "attn_fwd_kernel",
                      "xq_vit_residual_ln_bwd": "residual_ln_bwd_kernel", "xq_vit_residual_ln_fwd": "residual_ln_fwd_kernel",
-                     "xq_vit_gelu_fwd": "gelu_fwd_kernel", "xq_vit_gelu_bwd": "gelu_bwd_kernel"}
+                     "xq_vit_gelu_fwd": "gelu_fwd_kernel", "xq_vit_gelu_bwd": "gelu_bwd_kernel",
+                     "xq_vit_fc1_gelu_fwd": "mlp_gemm_kernel_fwd", "xq_vit_fc2_dgelu_bwd": "mlp_gemm_kernel_bwd"}
 
 
 def top_kernel_roofline(kern_table, hbm_peak, tf_peak, step_ms, ncu_traffic=None, src="measured"):
