@@ -14,10 +14,11 @@
 // (bias slice in shared memory, bias-gradient sums in registers, the weight tile hot in L2) and walks the 256-row blocks.
 // Warps 0-15 epilogue (TMEM lane quarter = warp % 4, 64 columns per warp group), warp 16 TMA producer, warp 17 MMA issuer
 // (leader CTA only).  Epilogue I/O goes through a per-warp 2 KB transposition buffer so that global accesses are full
-// 32-byte sectors (scattered 16-byte row stores cost 0.5 ms per output at this size).
+// 32-byte sectors (scattered 16-byte row stores cost 0.5 ms per output at this size); its arithmetic runs on packed fp32 pairs
+// (fma.rn.f32x2 -> FFMA2 / FMUL2 / FADD2, xq_gelu.cuh) because the epilogue, not the main loop, is what bounds the fused kernels.
 // Measured (tools/gemm_probe.cu, B200, M = 131328, N = 3072, K = 768): plain 0.456 ms = 1.36 PFLOP/s vs cuBLAS
-// nvjet_tst_128x256_64x6_2x1_2cta 0.434 ms (ratio 1.05, bit-identical results); fused forward 0.605 ms vs 0.69 ms for
-// cuBLAS + gelu_fwd_kernel; fused backward 0.764 ms vs 0.85 ms for cuBLAS + gelu_bwd_kernel.
+// nvjet_tst_128x256_64x6_2x1_2cta 0.434 ms (ratio 1.05, bit-identical results); fused forward 0.554 ms vs 0.72 ms for
+// cuBLAS + gelu_fwd_kernel; fused backward 0.670 ms vs 0.83 ms for cuBLAS + gelu_bwd_kernel (tools/mlp_gemm_bench.py).
 #include "xq_common.cuh"
 #include "xq_tc.cuh"
 #include "xq_gelu.cuh"
